@@ -1,0 +1,1262 @@
+// sb_api.cu -- host side of the C ABI declared in include/stenos_b200.h.
+//
+// Mirrors the reference's public API for the level-1 path (stenos/internal/stenos.cpp) on top of
+// the kernels of sb_kernels.cuh / sb_filters.cuh.  Frame logic that is not arithmetic on the data
+// (header layout, superblock sizing, error codes) follows stenos.cpp line by line (cited inline);
+// all data-path work runs on the GPU.  The only host-side data work is the Zstd coding of a final
+// superblock shorter than 128 bytes (stenos.cpp:435-437), which the reference delegates to libzstd
+// as well -- here through dlopen("libzstd.so.1").
+#include "sb_kernels.cuh"
+#include "sb_filters.cuh"
+#include "../../include/stenos_b200.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <dlfcn.h>
+
+namespace
+{
+	std::atomic<unsigned long long> g_launches{ 0 };
+
+	inline bool is_err(size_t r) { return r >= STENOS_LAST_ERROR_CODE; }
+
+	// ---- libzstd, only for the < 128 byte tail superblock ---------------------------------------
+	typedef size_t (*zstd_compress_fn)(void*, size_t, const void*, size_t, int);
+	typedef size_t (*zstd_decompress_fn)(void*, size_t, const void*, size_t);
+	typedef unsigned (*zstd_iserror_fn)(size_t);
+	zstd_compress_fn p_zstd_compress = nullptr;
+	zstd_decompress_fn p_zstd_decompress = nullptr;
+	zstd_iserror_fn p_zstd_iserror = nullptr;
+	bool load_zstd()
+	{
+		static std::atomic<int> state{ 0 }; // 0 untried, 1 ok, 2 missing
+		int s = state.load();
+		if (s == 0) {
+			void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+			if (h) {
+				p_zstd_compress = (zstd_compress_fn)dlsym(h, "ZSTD_compress");
+				p_zstd_decompress = (zstd_decompress_fn)dlsym(h, "ZSTD_decompress");
+				p_zstd_iserror = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
+			}
+			s = (p_zstd_compress && p_zstd_decompress && p_zstd_iserror) ? 1 : 2;
+			state.store(s);
+		}
+		return s == 1;
+	}
+
+	// ---- small RAII-free device buffer that only grows -----------------------------------------
+	struct DevBuf
+	{
+		uint8_t* p = nullptr;
+		size_t cap = 0;
+		bool reserve(size_t n)
+		{
+			if (n <= cap)
+				return true;
+			if (p)
+				cudaFree(p);
+			p = nullptr;
+			cap = 0;
+			size_t want = n + (n >> 3) + 256;
+			if (cudaMalloc((void**)&p, want) != cudaSuccess) {
+				cudaGetLastError();
+				p = nullptr;
+				if (cudaMalloc((void**)&p, n + 64) != cudaSuccess) {
+					cudaGetLastError();
+					p = nullptr;
+					return false;
+				}
+				want = n + 64;
+			}
+			cap = want;
+			return true;
+		}
+		void release()
+		{
+			if (p)
+				cudaFree(p);
+			p = nullptr;
+			cap = 0;
+		}
+	};
+
+	bool is_device_ptr(const void* p)
+	{
+		if (!p)
+			return false;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+			cudaGetLastError();
+			return false;
+		}
+		return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+	}
+
+	// super_block_size(), stenos.cpp:71-76
+	size_t default_superblock(size_t T)
+	{
+		const size_t bs = T * 256;
+		return bs > STENOS_BLOCK_SIZE ? bs : (STENOS_BLOCK_SIZE / bs) * bs;
+	}
+}
+
+struct stenos_context_s
+{
+	// parameters (stenos.cpp:94-98)
+	int level = 1;
+	int threads = 1;
+	uint64_t max_ns = 0;
+	size_t custom_shift = STENOS_NO_BLOCK_SHIFT;
+	// device additions
+	int device = -1;
+	cudaStream_t user_stream = nullptr;
+	bool has_user_stream = false;
+	cudaStream_t own_stream = nullptr;
+	bool own_stream_made = false;
+	// prepared state
+	size_t superblock = 0;
+	int shift = 0;
+	// scratch
+	DevBuf in, out, ctl, idx;
+	unsigned long long* host_result = nullptr; // pinned, 4 words
+	int sm_count = 0;
+
+	cudaStream_t stream()
+	{
+		if (has_user_stream)
+			return user_stream;
+		if (!own_stream_made) {
+			if (cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking) != cudaSuccess)
+				own_stream = nullptr;
+			own_stream_made = true;
+		}
+		return own_stream;
+	}
+	bool activate()
+	{
+		if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
+			cudaGetLastError();
+			return false;
+		}
+		if (!sm_count) {
+			int dev = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceProp prop;
+			if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+				cudaGetLastError();
+				return false;
+			}
+			sm_count = prop.multiProcessorCount;
+		}
+		if (!host_result) {
+			if (cudaMallocHost((void**)&host_result, 64) != cudaSuccess) {
+				cudaGetLastError();
+				host_result = nullptr;
+				return false;
+			}
+		}
+		return true;
+	}
+	// prepare(), stenos.cpp:115-185, without the time-limited branch
+	size_t prepare(size_t T, size_t bytes)
+	{
+		if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
+			return STENOS_ERROR_INVALID_BYTESOFTYPE;
+		const size_t block = T * 256;
+		size_t sb;
+		shift = 0;
+		if (custom_shift != STENOS_NO_BLOCK_SHIFT) {
+			sb = block << custom_shift;
+			shift = 255;
+		}
+		else {
+			sb = default_superblock(T);
+			if (bytes > sb) {
+				shift = level ? (level - 1) / 2 : 0;
+				sb <<= (size_t)shift;
+			}
+		}
+		if (sb < block || sb >= STENOS_MAX_BLOCK_BYTES)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		superblock = sb;
+		return 0;
+	}
+	void free_all()
+	{
+		in.release();
+		out.release();
+		ctl.release();
+		idx.release();
+		if (host_result)
+			cudaFreeHost(host_result);
+		host_result = nullptr;
+		if (own_stream_made && own_stream)
+			cudaStreamDestroy(own_stream);
+		own_stream = nullptr;
+		own_stream_made = false;
+	}
+};
+
+namespace
+{
+	using namespace sb;
+
+	bool supported_T(size_t T) { return T == 2 || T == 4 || T == 8; }
+
+	// ---- launchers ------------------------------------------------------------------------------
+	template<int T>
+	size_t launch_encode_T(stenos_context* ctx, const EncodeParams& P)
+	{
+		const int nthreads = 512;
+		const uint32_t smem = EncodeLayout<T>::smem_bytes(nthreads / 32);
+		if (cudaFuncSetAttribute(encode_frame_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_ALLOC;
+		}
+		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, ctx->sm_count));
+		STENOS_LAUNCH(encode_frame_kernel<T>, dim3(grid), dim3(nthreads), smem, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+	size_t launch_encode(stenos_context* ctx, size_t T, const EncodeParams& P)
+	{
+		switch (T) {
+			case 2: return launch_encode_T<2>(ctx, P);
+			case 4: return launch_encode_T<4>(ctx, P);
+			case 8: return launch_encode_T<8>(ctx, P);
+		}
+		return STENOS_ERROR_INVALID_PARAMETER;
+	}
+	template<int T>
+	size_t launch_decode_T(stenos_context* ctx, const DecodeParams& P)
+	{
+		const unsigned grid = (P.n_sb + DECODE_WARPS - 1) / DECODE_WARPS;
+		STENOS_LAUNCH(decode_frame_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+	size_t launch_decode(stenos_context* ctx, size_t T, const DecodeParams& P)
+	{
+		if (!P.n_sb)
+			return 0;
+		switch (T) {
+			case 2: return launch_decode_T<2>(ctx, P);
+			case 4: return launch_decode_T<4>(ctx, P);
+			case 8: return launch_decode_T<8>(ctx, P);
+		}
+		return STENOS_ERROR_INVALID_PARAMETER;
+	}
+	template<int T>
+	size_t launch_gather_T(stenos_context* ctx, const GatherParams& P)
+	{
+		const unsigned grid = (P.n + DECODE_WARPS - 1) / DECODE_WARPS;
+		STENOS_LAUNCH(gather_decode_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+
+	// control block in device memory: [result:2 x u64][ticket u32 + pad][state: n_sb x u64]
+	struct Control
+	{
+		unsigned long long* result;
+		uint32_t* ticket;
+		unsigned long long* state;
+	};
+	bool make_control(stenos_context* ctx, size_t n_sb, Control& c, bool zero_result)
+	{
+		const size_t bytes = 32 + n_sb * 8;
+		if (!ctx->ctl.reserve(bytes))
+			return false;
+		c.result = reinterpret_cast<unsigned long long*>(ctx->ctl.p);
+		c.ticket = reinterpret_cast<uint32_t*>(ctx->ctl.p + 16);
+		c.state = reinterpret_cast<unsigned long long*>(ctx->ctl.p + 32);
+		if (zero_result)
+			cudaMemsetAsync(ctx->ctl.p, 0, bytes, ctx->stream());
+		else
+			cudaMemsetAsync(ctx->ctl.p + 16, 0, bytes - 16, ctx->stream());
+		return true;
+	}
+
+	size_t map_device_error(unsigned long long bits)
+	{
+		if (bits & DEV_ERR_DST_OVERFLOW)
+			return STENOS_ERROR_DST_OVERFLOW;
+		if (bits & DEV_ERR_SRC_OVERFLOW)
+			return STENOS_ERROR_SRC_OVERFLOW;
+		if (bits & DEV_ERR_INVALID_INPUT)
+			return STENOS_ERROR_INVALID_INPUT;
+		return 0;
+	}
+
+	// Enqueues the encoder for `bytes` (whole superblocks, each >= 128 bytes or level 0) of a frame
+	// or segment.  d_result: device [2] words, zeroed here.
+	size_t enqueue_encode(stenos_context* ctx, const uint8_t* d_src, size_t T, size_t bytes, uint8_t* d_dst, size_t dst_size, size_t sb, uint32_t header_len,
+			      uint32_t shift_byte, uint64_t frame_bytes, int level, unsigned long long* d_result, unsigned long long* d_sb_offsets)
+	{
+		const size_t n_sb = (bytes + sb - 1) / sb;
+		if (!n_sb)
+			return 0;
+		if (n_sb > 0xFFFFFFF0ull)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		Control c;
+		if (!make_control(ctx, n_sb, c, d_result == nullptr))
+			return STENOS_ERROR_ALLOC;
+		if (d_result)
+			cudaMemsetAsync(d_result, 0, 16, ctx->stream());
+		EncodeParams P;
+		P.src = d_src;
+		P.bytes = bytes;
+		P.dst = d_dst;
+		P.dst_size = dst_size;
+		P.sb_bytes = (uint32_t)sb;
+		P.n_sb = (uint32_t)n_sb;
+		P.header_len = header_len;
+		P.shift_byte = shift_byte;
+		P.frame_bytes = frame_bytes;
+		P.level = level;
+		P.state = c.state;
+		P.ticket = c.ticket;
+		P.result = d_result ? d_result : c.result;
+		P.sb_offsets = d_sb_offsets;
+		P.base_offset = 0;
+		return launch_encode(ctx, T, P);
+	}
+
+	bool write_frame_header(uint8_t* h, int shift, uint64_t bytes, size_t sb, bool custom)
+	{
+		// stenos.cpp:862-874
+		h[0] = (uint8_t)shift;
+		for (int i = 0; i < 7; ++i)
+			h[1 + i] = (uint8_t)(bytes >> (8 * i));
+		if (custom)
+			for (int i = 0; i < 4; ++i)
+				h[8 + i] = (uint8_t)(sb >> (8 * i));
+		return true;
+	}
+
+	// Common body of stenos_compress_generic and stenos_private_compress_block.
+	// frame = true : [frame header] + superblocks;   frame = false: one bare superblock
+	size_t compress_impl(stenos_context* ctx, const void* src_, size_t T, size_t bytes, void* dst_, size_t dst_size, bool frame, size_t sb)
+	{
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		if (ctx->max_ns != 0)
+			return STENOS_ERROR_INVALID_PARAMETER; // time limited compression is wall-clock driven: out of scope
+		const int level = ctx->level;
+		if (level > 1 || !supported_T(T))
+			return STENOS_ERROR_INVALID_PARAMETER; // no CPU fallback: levels >= 2 need Zstd
+		if (sb > STENOS_BLOCK_SIZE)
+			return STENOS_ERROR_INVALID_PARAMETER; // shared-memory slots hold at most 128 KiB superblocks
+		const uint8_t* src = static_cast<const uint8_t*>(src_);
+		uint8_t* dst = static_cast<uint8_t*>(dst_);
+		const bool custom = ctx->custom_shift != STENOS_NO_BLOCK_SHIFT;
+		const uint32_t header_len = frame ? (custom ? 12u : 8u) : 0u;
+		cudaStream_t st = ctx->stream();
+
+		if (frame) {
+			// stenos.cpp:862-878
+			if (dst_size < 8 || (custom && dst_size < 12))
+				return STENOS_ERROR_DST_OVERFLOW;
+			if (bytes == 0) {
+				uint8_t h[12];
+				write_frame_header(h, ctx->shift, 0, sb, custom);
+				if (is_device_ptr(dst)) {
+					cudaMemcpyAsync(dst, h, header_len, cudaMemcpyHostToDevice, st);
+					cudaStreamSynchronize(st);
+				}
+				else
+					memcpy(dst, h, header_len);
+				return header_len;
+			}
+		}
+		else if (dst_size < 4)
+			return STENOS_ERROR_DST_OVERFLOW; // stenos.cpp:427-429
+
+		const bool src_dev = is_device_ptr(src), dst_dev = is_device_ptr(dst);
+		// the tail superblock shorter than 128 bytes goes through libzstd on the host (stenos.cpp:435-437)
+		const size_t n_sb = bytes ? (bytes + sb - 1) / sb : (frame ? 0 : 1);
+		const size_t last_bytes = bytes - (n_sb ? (n_sb - 1) * sb : 0);
+		const bool host_tail = level >= 1 && n_sb && last_bytes < 128 && bytes != 0;
+		const size_t dev_bytes = host_tail ? bytes - last_bytes : bytes;
+
+		// ---- stage input
+		const uint8_t* d_src = src;
+		if (dev_bytes) {
+			if (!src_dev || ((uintptr_t)src & 15u)) {
+				if (!ctx->in.reserve(dev_bytes + 16))
+					return STENOS_ERROR_ALLOC;
+				cudaMemcpyAsync(ctx->in.p, src, dev_bytes, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+				d_src = ctx->in.p;
+			}
+		}
+		// ---- output
+		uint8_t* d_dst = dst;
+		size_t d_cap = dst_size;
+		if (!dst_dev) {
+			// The staging buffer never needs more than the worst case of the frame (every superblock
+			// stored as COPY); the kernel still receives the caller's dst_size because the reference's
+			// room arithmetic depends on it.
+			const size_t alloc = std::min(dst_size, (size_t)header_len + n_sb * 4 + bytes + 16);
+			if (!ctx->out.reserve(alloc + 16))
+				return STENOS_ERROR_ALLOC;
+			d_dst = ctx->out.p;
+		}
+
+		size_t total = header_len;
+		if (dev_bytes || (bytes == 0 && !frame)) {
+			size_t r;
+			if (bytes == 0) {
+				// empty bare superblock: [6][0:3] (stenos.cpp:431-433)
+				const uint8_t h[4] = { (uint8_t)CODE_COPY, 0, 0, 0 };
+				cudaMemcpyAsync(d_dst, h, 4, cudaMemcpyHostToDevice, st);
+				cudaStreamSynchronize(st);
+				total = 4;
+				r = 0;
+			}
+			else {
+				r = enqueue_encode(ctx, d_src, T, dev_bytes, d_dst, d_cap, sb, header_len, (uint32_t)ctx->shift, bytes, level, nullptr, nullptr);
+				if (is_err(r))
+					return r;
+				cudaMemcpyAsync(ctx->host_result, ctx->ctl.p, 16, cudaMemcpyDeviceToHost, st);
+				if (cudaStreamSynchronize(st) != cudaSuccess) {
+					cudaGetLastError();
+					return STENOS_ERROR_UNDEFINED;
+				}
+				const size_t e = map_device_error(ctx->host_result[1]);
+				if (e)
+					return e;
+				total = (size_t)ctx->host_result[0];
+			}
+		}
+		else if (frame) {
+			// only a tiny tail: the header is written from the host
+			uint8_t h[12];
+			write_frame_header(h, ctx->shift, bytes, sb, custom);
+			cudaMemcpyAsync(d_dst, h, header_len, cudaMemcpyHostToDevice, st);
+		}
+
+		if (host_tail) {
+			uint8_t tail[128], enc[4 + 256];
+			if (src_dev) {
+				cudaMemcpyAsync(tail, src + dev_bytes, last_bytes, cudaMemcpyDeviceToHost, st);
+				cudaStreamSynchronize(st);
+			}
+			else
+				memcpy(tail, src + dev_bytes, last_bytes);
+			if (total + 4 > dst_size)
+				return STENOS_ERROR_DST_OVERFLOW;
+			size_t len = 0;
+			bool zok = false;
+			if (!load_zstd())
+				return STENOS_ERROR_ZSTD_INTERNAL;
+			// zstd_compress_with_context(dst + 4, dst_size - 4, src, bytes, 0) -> zstd level 1 (zstd_wrapper.h:49-56)
+			const size_t room = std::min<size_t>(dst_size - total - 4, 256);
+			const size_t zr = p_zstd_compress(enc + 4, room, tail, last_bytes, 1);
+			if (!p_zstd_iserror(zr) && zr <= last_bytes) {
+				zok = true;
+				len = zr;
+				enc[0] = (uint8_t)CODE_ZSTD;
+			}
+			if (!zok) { // stenos.cpp:668-669 -> MEMCPY
+				if (dst_size - total < last_bytes + 4)
+					return STENOS_ERROR_DST_OVERFLOW;
+				enc[0] = (uint8_t)CODE_COPY;
+				memcpy(enc + 4, tail, last_bytes);
+				len = last_bytes;
+			}
+			enc[1] = (uint8_t)len;
+			enc[2] = (uint8_t)(len >> 8);
+			enc[3] = (uint8_t)(len >> 16);
+			cudaMemcpyAsync(d_dst + total, enc, len + 4, cudaMemcpyHostToDevice, st);
+			cudaStreamSynchronize(st);
+			total += len + 4;
+		}
+		if (!dst_dev) {
+			cudaMemcpyAsync(dst, d_dst, total, cudaMemcpyDeviceToHost, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+		}
+		return total;
+	}
+
+	// host walk over the superblock headers (stenos.cpp:1124-1143); returns 0 or an error code
+	size_t host_frame_index(const uint8_t* src, size_t size, size_t first, size_t n_sb, unsigned long long* offs)
+	{
+		size_t at = first;
+		for (size_t i = 0; i < n_sb; ++i) {
+			if (at + 4 > size)
+				return STENOS_ERROR_SRC_OVERFLOW;
+			offs[i] = at;
+			const size_t csize = (size_t)src[at + 1] | ((size_t)src[at + 2] << 8) | ((size_t)src[at + 3] << 16);
+			if (at + 4 + csize > size)
+				return STENOS_ERROR_INVALID_INPUT;
+			at += 4 + csize;
+		}
+		offs[n_sb] = at;
+		return 0;
+	}
+
+	size_t decompress_impl(stenos_context* ctx, const void* src_, size_t T, size_t size, void* dst_, size_t dst_size, bool frame, size_t bare_sb)
+	{
+		if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
+			return STENOS_ERROR_INVALID_BYTESOFTYPE; // stenos.cpp:1067-1068
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		const uint8_t* src = static_cast<const uint8_t*>(src_);
+		uint8_t* dst = static_cast<uint8_t*>(dst_);
+		const bool src_dev = is_device_ptr(src), dst_dev = is_device_ptr(dst);
+		cudaStream_t st = ctx->stream();
+
+		uint64_t total;
+		size_t sb, first;
+		if (frame) {
+			// stenos.cpp:1078-1107
+			if (size < 8)
+				return STENOS_ERROR_SRC_OVERFLOW;
+			uint8_t h[12] = { 0 };
+			const size_t hl = std::min<size_t>(size, 12);
+			if (src_dev) {
+				cudaMemcpyAsync(h, src, hl, cudaMemcpyDeviceToHost, st);
+				cudaStreamSynchronize(st);
+			}
+			else
+				memcpy(h, src, hl);
+			const unsigned shift = h[0];
+			if (shift > 4 && shift != 255)
+				return STENOS_ERROR_INVALID_INPUT;
+			total = 0;
+			for (int i = 0; i < 7; ++i)
+				total |= (uint64_t)h[1 + i] << (8 * i);
+			if (total > dst_size)
+				return STENOS_ERROR_DST_OVERFLOW;
+			if (total == 0)
+				return 0;
+			first = 8;
+			if (shift == 255) {
+				if (size < 12)
+					return STENOS_ERROR_SRC_OVERFLOW;
+				sb = (size_t)h[8] | ((size_t)h[9] << 8) | ((size_t)h[10] << 16) | ((size_t)h[11] << 24);
+				first = 12;
+				if (sb == 0)
+					return STENOS_ERROR_INVALID_INPUT;
+			}
+			else
+				sb = default_superblock(T) << shift;
+		}
+		else {
+			// stenos_private_decompress_block, stenos.cpp:780-804: one superblock, dsize = dst_size
+			if (size < 4)
+				return STENOS_ERROR_SRC_OVERFLOW;
+			total = dst_size;
+			sb = std::max<size_t>(bare_sb, 1);
+			if (total > sb)
+				sb = total;
+			first = 0;
+			if (total == 0)
+				return 0;
+		}
+		if (!supported_T(T))
+			return STENOS_ERROR_INVALID_PARAMETER;
+		const size_t n_sb = (size_t)((total + sb - 1) / sb);
+		if (n_sb > 0xFFFFFFF0ull)
+			return STENOS_ERROR_INVALID_PARAMETER;
+
+		// ---- stage the compressed bytes and build the superblock index
+		const uint8_t* d_src = src;
+		if (!ctx->idx.reserve((n_sb + 1) * 8))
+			return STENOS_ERROR_ALLOC;
+		unsigned long long* d_offs = reinterpret_cast<unsigned long long*>(ctx->idx.p);
+		if (!ctx->ctl.reserve(64))
+			return STENOS_ERROR_ALLOC;
+		unsigned long long* d_result = reinterpret_cast<unsigned long long*>(ctx->ctl.p);
+		cudaMemsetAsync(d_result, 0, 16, st);
+		unsigned last_code = 0;
+		size_t last_at = 0, last_csize = 0;
+		if (!src_dev) {
+			unsigned long long* offs = (unsigned long long*)malloc((n_sb + 1) * 8);
+			if (!offs)
+				return STENOS_ERROR_ALLOC;
+			const size_t e = host_frame_index(src, size, first, n_sb, offs);
+			if (e) {
+				free(offs);
+				return e;
+			}
+			last_at = (size_t)offs[n_sb - 1];
+			last_code = src[last_at];
+			last_csize = (size_t)(offs[n_sb] - offs[n_sb - 1]) - 4;
+			const size_t used = (size_t)offs[n_sb];
+			if (!ctx->in.reserve(used + 32)) {
+				free(offs);
+				return STENOS_ERROR_ALLOC;
+			}
+			cudaMemcpyAsync(ctx->in.p, src, used, cudaMemcpyHostToDevice, st);
+			cudaMemcpyAsync(d_offs, offs, (n_sb + 1) * 8, cudaMemcpyHostToDevice, st);
+			cudaStreamSynchronize(st); // offs is pageable: the copy above is staged before returning, but keep it simple
+			free(offs);
+			d_src = ctx->in.p;
+			size = used;
+		}
+		else {
+			IndexParams I;
+			I.src = src;
+			I.src_size = size;
+			I.first = first;
+			I.n_sb = (uint32_t)n_sb;
+			I.sb_offsets = d_offs;
+			I.result = d_result;
+			STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
+			++g_launches;
+		}
+
+		// ---- output
+		uint8_t* d_dst = dst;
+		if (!dst_dev || ((uintptr_t)dst & 15u)) {
+			if (!ctx->out.reserve((size_t)total + 32))
+				return STENOS_ERROR_ALLOC;
+			d_dst = ctx->out.p;
+		}
+		DecodeParams P;
+		P.src = d_src;
+		P.src_size = size;
+		P.dst = d_dst;
+		P.total = total;
+		P.sb_bytes = (uint32_t)sb;
+		P.n_sb = (uint32_t)n_sb;
+		P.first_sb = 0;
+		P.sb_offsets = d_offs;
+		P.result = d_result;
+		P.skip_zstd_tail = 1;
+		P.dst_origin = 0;
+		const size_t lr = launch_decode(ctx, T, P);
+		if (is_err(lr))
+			return lr;
+		cudaMemcpyAsync(ctx->host_result, d_result, 16, cudaMemcpyDeviceToHost, st);
+		// the last superblock may be a Zstd coded tail (< 128 bytes): needs its header on the host
+		const size_t last_dsize = (size_t)(total - (uint64_t)(n_sb - 1) * sb);
+		uint8_t tail_hdr[4 + 256];
+		if (src_dev && last_dsize < 128) {
+			cudaMemcpyAsync(ctx->host_result + 2, d_offs + (n_sb - 1), 16, cudaMemcpyDeviceToHost, st);
+			cudaStreamSynchronize(st);
+			last_at = (size_t)ctx->host_result[2];
+			if (last_at + 4 <= size) {
+				cudaMemcpyAsync(tail_hdr, src + last_at, std::min<size_t>(size - last_at, sizeof(tail_hdr)), cudaMemcpyDeviceToHost, st);
+				cudaStreamSynchronize(st);
+				last_code = tail_hdr[0];
+				last_csize = (size_t)tail_hdr[1] | ((size_t)tail_hdr[2] << 8) | ((size_t)tail_hdr[3] << 16);
+			}
+		}
+		if (cudaStreamSynchronize(st) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_UNDEFINED;
+		}
+		const size_t e = map_device_error(ctx->host_result[1]);
+		if (e)
+			return frame ? e : STENOS_ERROR_INVALID_INPUT;
+		if (last_dsize < 128 && last_code == (unsigned)CODE_ZSTD) {
+			// stenos.cpp:694-699
+			if (!load_zstd())
+				return STENOS_ERROR_ZSTD_INTERNAL;
+			if (last_csize > 256 || last_at + 4 + last_csize > size)
+				return STENOS_ERROR_INVALID_INPUT;
+			uint8_t dec[128];
+			const uint8_t* payload;
+			if (src_dev)
+				payload = tail_hdr + 4;
+			else
+				payload = src + last_at + 4;
+			const size_t zr = p_zstd_decompress(dec, last_dsize, payload, last_csize);
+			if (p_zstd_iserror(zr) || zr != last_dsize)
+				return STENOS_ERROR_INVALID_INPUT;
+			cudaMemcpyAsync(d_dst + (total - last_dsize), dec, last_dsize, cudaMemcpyHostToDevice, st);
+			cudaStreamSynchronize(st);
+		}
+		if (d_dst != dst) {
+			cudaMemcpyAsync(dst, d_dst, (size_t)total, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+		}
+		return (size_t)total;
+	}
+
+	template<class F>
+	size_t guarded(F&& f) noexcept
+	{
+		try {
+			return f();
+		}
+		catch (...) {
+			return STENOS_ERROR_ALLOC; // stenos.cpp:190-199
+		}
+	}
+}
+
+extern "C" {
+
+stenos_context* stenos_make_context(void)
+{
+	void* m = malloc(sizeof(stenos_context_s));
+	if (!m)
+		return nullptr;
+	return new (m) stenos_context_s();
+}
+void stenos_destroy_context(stenos_context* ctx)
+{
+	if (ctx) {
+		if (ctx->device >= 0)
+			cudaSetDevice(ctx->device);
+		ctx->free_all();
+		ctx->~stenos_context_s();
+		free(ctx);
+	}
+}
+void stenos_reset_context(stenos_context* ctx)
+{
+	if (ctx) {
+		ctx->level = 1;
+		ctx->threads = 1;
+		ctx->max_ns = 0;
+	}
+}
+size_t stenos_set_level(stenos_context* ctx, int level)
+{
+	ctx->level = level > 9 ? 9 : (level < 0 ? 0 : level);
+	return 0;
+}
+size_t stenos_set_threads(stenos_context* ctx, int threads)
+{
+	ctx->threads = threads < 1 ? 1 : threads;
+	return 0;
+}
+size_t stenos_set_max_nanoseconds(stenos_context* ctx, uint64_t nanoseconds)
+{
+	ctx->max_ns = nanoseconds;
+	return 0;
+}
+size_t stenos_set_block_size(stenos_context* ctx, size_t blocksize_shift)
+{
+	if (blocksize_shift >= 16 && blocksize_shift != STENOS_NO_BLOCK_SHIFT)
+		return STENOS_ERROR_INVALID_PARAMETER;
+	ctx->custom_shift = blocksize_shift;
+	return 0;
+}
+size_t stenos_memory_footprint(stenos_context* ctx)
+{
+	return sizeof(stenos_context_s) + ctx->in.cap + ctx->out.cap + ctx->ctl.cap + ctx->idx.cap + (ctx->host_result ? 64 : 0);
+}
+int stenos_has_error(size_t r)
+{
+	return r >= STENOS_LAST_ERROR_CODE;
+}
+size_t stenos_bound(size_t bytes)
+{
+	const size_t min_superblock = 65792;
+	const size_t n = bytes / min_superblock + (bytes % min_superblock ? 1 : 0);
+	return 12 + (n == 0 ? 1 : n) * 4 + bytes;
+}
+
+size_t stenos_compress_generic(stenos_context* ctx, const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size)
+{
+	return guarded([&]() -> size_t {
+		const size_t prep = ctx->prepare(bytesoftype, bytes);
+		if (is_err(prep))
+			return prep;
+		return compress_impl(ctx, src, bytesoftype, bytes, dst, dst_size, true, ctx->superblock);
+	});
+}
+size_t stenos_decompress_generic(stenos_context* ctx, const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size)
+{
+	return guarded([&]() -> size_t { return decompress_impl(ctx, src, bytesoftype, bytes, dst, dst_size, true, 0); });
+}
+size_t stenos_compress(const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size, int level)
+{
+	stenos_context_s ctx;
+	ctx.level = level > 9 ? 9 : (level < 0 ? 0 : level);
+	const size_t r = stenos_compress_generic(&ctx, src, bytesoftype, bytes, dst, dst_size);
+	ctx.free_all();
+	return r;
+}
+size_t stenos_decompress(const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size)
+{
+	stenos_context_s ctx;
+	const size_t r = stenos_decompress_generic(&ctx, src, bytesoftype, bytes, dst, dst_size);
+	ctx.free_all();
+	return r;
+}
+size_t stenos_get_info(const void* src_, size_t bytesoftype, size_t bytes, stenos_info* info)
+{
+	// stenos.cpp:1019-1050
+	const uint8_t* src = static_cast<const uint8_t*>(src_);
+	if (bytes < 8)
+		return STENOS_ERROR_SRC_OVERFLOW;
+	const unsigned shift = src[0];
+	if (shift > 4 && shift != 255)
+		return STENOS_ERROR_INVALID_INPUT;
+	uint64_t total = 0;
+	for (int i = 0; i < 7; ++i)
+		total |= (uint64_t)src[1 + i] << (8 * i);
+	info->decompressed_size = (size_t)total;
+	if (shift == 255) {
+		if (bytes < 12)
+			return STENOS_ERROR_SRC_OVERFLOW;
+		info->superblock_size = (size_t)src[8] | ((size_t)src[9] << 8) | ((size_t)src[10] << 16) | ((size_t)src[11] << 24);
+		return 12;
+	}
+	info->superblock_size = default_superblock(bytesoftype) << shift;
+	return 8;
+}
+
+struct stenos_timer_s
+{
+	std::chrono::steady_clock::time_point t0;
+};
+stenos_timer* stenos_make_timer(void)
+{
+	stenos_timer* t = (stenos_timer*)malloc(sizeof(stenos_timer_s));
+	if (!t)
+		return nullptr;
+	new (t) stenos_timer_s();
+	t->t0 = std::chrono::steady_clock::now();
+	return t;
+}
+void stenos_destroy_timer(stenos_timer* timer)
+{
+	if (timer)
+		free(timer);
+}
+void stenos_tick(stenos_timer* timer)
+{
+	timer->t0 = std::chrono::steady_clock::now();
+}
+uint64_t stenos_tock(stenos_timer* timer)
+{
+	return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - timer->t0).count();
+}
+
+size_t stenos_private_compress_block(stenos_context* ctx, const void* src, size_t bytesoftype, size_t super_block_size, size_t bytes, void* dst, size_t dst_size)
+{
+	return guarded([&]() -> size_t {
+		if (bytesoftype == 0 || bytesoftype >= STENOS_MAX_BYTESOFTYPE)
+			return STENOS_ERROR_INVALID_BYTESOFTYPE;
+		if (bytes > super_block_size)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		ctx->superblock = super_block_size;
+		return compress_impl(ctx, src, bytesoftype, bytes, dst, dst_size, false, std::max<size_t>(super_block_size, 1));
+	});
+}
+size_t stenos_private_decompress_block(stenos_context* ctx, const void* src, size_t bytesoftype, size_t super_block_size, size_t bytes, void* dst, size_t dst_size)
+{
+	return guarded([&]() -> size_t {
+		ctx->superblock = super_block_size;
+		return decompress_impl(ctx, src, bytesoftype, bytes, dst, dst_size, false, super_block_size);
+	});
+}
+size_t stenos_private_block_size(const void* src_, size_t src_size)
+{
+	if (src_size < 4)
+		return STENOS_ERROR_SRC_OVERFLOW;
+	const uint8_t* s = static_cast<const uint8_t*>(src_);
+	return ((size_t)s[1] | ((size_t)s[2] << 8) | ((size_t)s[3] << 16)) + 4;
+}
+size_t stenos_private_block_csize(const void* src_)
+{
+	if (!src_)
+		return 0;
+	const uint8_t* s = static_cast<const uint8_t*>(src_);
+	return ((size_t)s[1] | ((size_t)s[2] << 8) | ((size_t)s[3] << 16)) + 4;
+}
+size_t stenos_private_create_compression_header(size_t decompressed_size, size_t super_block_size, void* dst_, size_t dst_size)
+{
+	if (dst_size < 12)
+		return STENOS_ERROR_DST_OVERFLOW;
+	write_frame_header(static_cast<uint8_t*>(dst_), 255, decompressed_size, super_block_size, true);
+	return 12;
+}
+
+// ---- device additions -----------------------------------------------------------------------
+
+size_t stenos_set_device(stenos_context* ctx, int device)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return STENOS_ERROR_INVALID_PARAMETER;
+	}
+	if (device >= n)
+		return STENOS_ERROR_INVALID_PARAMETER;
+	if (device != ctx->device) {
+		ctx->free_all();
+		ctx->sm_count = 0;
+	}
+	ctx->device = device < 0 ? -1 : device;
+	return 0;
+}
+size_t stenos_set_stream(stenos_context* ctx, void* cuda_stream)
+{
+	ctx->user_stream = (cudaStream_t)cuda_stream;
+	ctx->has_user_stream = true;
+	return 0;
+}
+
+static size_t check_async_args(stenos_context* ctx, size_t T, const void* aligned_ptr)
+{
+	if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
+		return STENOS_ERROR_INVALID_BYTESOFTYPE;
+	if (!supported_T(T) || ctx->level > 1 || ctx->max_ns)
+		return STENOS_ERROR_INVALID_PARAMETER;
+	if ((uintptr_t)aligned_ptr & 15u)
+		return STENOS_ERROR_INVALID_PARAMETER;
+	return ctx->activate() ? 0 : STENOS_ERROR_ALLOC;
+}
+
+size_t stenos_b200_superblock_size(stenos_context* ctx, size_t bytesoftype, size_t bytes)
+{
+	const size_t r = ctx->prepare(bytesoftype, bytes);
+	return is_err(r) ? r : ctx->superblock;
+}
+
+size_t stenos_b200_compress_async(stenos_context* ctx, const void* d_src, size_t T, size_t bytes, void* d_dst, size_t dst_size, unsigned long long* d_result,
+				  unsigned long long* d_sb_offsets)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, d_src);
+		if (r)
+			return r;
+		r = ctx->prepare(T, bytes);
+		if (is_err(r))
+			return r;
+		const size_t sb = ctx->superblock;
+		if (sb > STENOS_BLOCK_SIZE || !d_result || bytes == 0)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		const size_t last = bytes - ((bytes - 1) / sb) * sb;
+		if (last < 128 && ctx->level >= 1)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		const bool custom = ctx->custom_shift != STENOS_NO_BLOCK_SHIFT;
+		if (dst_size < (custom ? 12u : 8u))
+			return STENOS_ERROR_DST_OVERFLOW;
+		return enqueue_encode(ctx, (const uint8_t*)d_src, T, bytes, (uint8_t*)d_dst, dst_size, sb, custom ? 12u : 8u, (uint32_t)ctx->shift, bytes, ctx->level, d_result,
+				      d_sb_offsets);
+	});
+}
+
+size_t stenos_b200_compress_segment_async(stenos_context* ctx, const void* d_src, size_t T, size_t seg_bytes, void* d_dst, size_t dst_size, unsigned long long* d_result,
+					  unsigned long long* d_sb_offsets)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, d_src);
+		if (r)
+			return r;
+		if (!ctx->superblock || !d_result || seg_bytes == 0)
+			return STENOS_ERROR_INVALID_PARAMETER; // call stenos_b200_superblock_size() with the FRAME size first
+		const size_t sb = ctx->superblock;
+		const size_t last = seg_bytes - ((seg_bytes - 1) / sb) * sb;
+		if (sb > STENOS_BLOCK_SIZE || (last < 128 && ctx->level >= 1))
+			return STENOS_ERROR_INVALID_PARAMETER;
+		return enqueue_encode(ctx, (const uint8_t*)d_src, T, seg_bytes, (uint8_t*)d_dst, dst_size, sb, 0, 0, 0, ctx->level, d_result, d_sb_offsets);
+	});
+}
+
+size_t stenos_b200_frame_index_async(stenos_context* ctx, const void* d_frame, size_t frame_bytes, size_t T, unsigned long long* d_sb_offsets, size_t capacity,
+				     unsigned long long* d_result)
+{
+	return guarded([&]() -> size_t {
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		cudaStream_t st = ctx->stream();
+		uint8_t h[12] = { 0 };
+		if (frame_bytes < 8)
+			return STENOS_ERROR_SRC_OVERFLOW;
+		cudaMemcpyAsync(h, d_frame, std::min<size_t>(frame_bytes, 12), cudaMemcpyDeviceToHost, st);
+		cudaStreamSynchronize(st);
+		stenos_info info;
+		const size_t first = stenos_get_info(h, T, std::min<size_t>(frame_bytes, 12), &info);
+		if (is_err(first))
+			return first;
+		if (!info.superblock_size)
+			return STENOS_ERROR_INVALID_INPUT;
+		const size_t n_sb = (info.decompressed_size + info.superblock_size - 1) / info.superblock_size;
+		if (n_sb + 1 > capacity)
+			return STENOS_ERROR_DST_OVERFLOW;
+		cudaMemsetAsync(d_result, 0, 16, st);
+		IndexParams I;
+		I.src = (const uint8_t*)d_frame;
+		I.src_size = frame_bytes;
+		I.first = first;
+		I.n_sb = (uint32_t)n_sb;
+		I.sb_offsets = d_sb_offsets;
+		I.result = d_result;
+		STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
+		++g_launches;
+		return n_sb;
+	});
+}
+
+size_t stenos_b200_decompress_range_async(stenos_context* ctx, const void* d_frame, size_t frame_bytes, size_t T, size_t decompressed_bytes, size_t first_sb, size_t n_sb,
+					  const unsigned long long* d_sb_offsets, void* d_dst, unsigned long long* d_result)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, d_dst);
+		if (r)
+			return r;
+		if (!ctx->superblock || !d_sb_offsets || !d_result)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		cudaMemsetAsync(d_result, 0, 16, ctx->stream());
+		DecodeParams P;
+		P.src = (const uint8_t*)d_frame;
+		P.src_size = frame_bytes;
+		P.dst = (uint8_t*)d_dst;
+		P.total = decompressed_bytes;
+		P.sb_bytes = (uint32_t)ctx->superblock;
+		P.n_sb = (uint32_t)n_sb;
+		P.first_sb = (uint32_t)first_sb;
+		P.sb_offsets = d_sb_offsets;
+		P.result = d_result;
+		P.skip_zstd_tail = 0;
+		P.dst_origin = (uint64_t)first_sb * ctx->superblock;
+		return launch_decode(ctx, T, P);
+	});
+}
+
+size_t stenos_b200_decompress_async(stenos_context* ctx, const void* d_src, size_t T, size_t bytes, void* d_dst, size_t dst_size, size_t decompressed_bytes,
+				    unsigned long long* d_result, const unsigned long long* d_sb_offsets)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, d_dst);
+		if (r)
+			return r;
+		if (!d_result || decompressed_bytes > dst_size)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		// superblock size as the compressor chose it for this size (level <= 1 -> shift 0)
+		const int saved = ctx->level;
+		ctx->level = 1;
+		r = ctx->prepare(T, decompressed_bytes);
+		ctx->level = saved;
+		if (is_err(r))
+			return r;
+		const size_t sb = ctx->superblock;
+		const size_t n_sb = (decompressed_bytes + sb - 1) / sb;
+		cudaStream_t st = ctx->stream();
+		cudaMemsetAsync(d_result, 0, 16, st);
+		const unsigned long long* offs = d_sb_offsets;
+		if (!offs) {
+			if (!ctx->idx.reserve((n_sb + 1) * 8))
+				return STENOS_ERROR_ALLOC;
+			IndexParams I;
+			I.src = (const uint8_t*)d_src;
+			I.src_size = bytes;
+			I.first = ctx->custom_shift != STENOS_NO_BLOCK_SHIFT ? 12 : 8;
+			I.n_sb = (uint32_t)n_sb;
+			I.sb_offsets = reinterpret_cast<unsigned long long*>(ctx->idx.p);
+			I.result = d_result;
+			STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
+			++g_launches;
+			offs = I.sb_offsets;
+		}
+		DecodeParams P;
+		P.src = (const uint8_t*)d_src;
+		P.src_size = bytes;
+		P.dst = (uint8_t*)d_dst;
+		P.total = decompressed_bytes;
+		P.sb_bytes = (uint32_t)sb;
+		P.n_sb = (uint32_t)n_sb;
+		P.first_sb = 0;
+		P.sb_offsets = offs;
+		P.result = d_result;
+		P.skip_zstd_tail = 0;
+		P.dst_origin = 0;
+		return launch_decode(ctx, T, P);
+	});
+}
+
+size_t stenos_b200_gather_decode_async(stenos_context* ctx, const void* d_frame, size_t frame_bytes, size_t T, size_t bucket_bytes, size_t decompressed_bytes,
+				       const unsigned long long* d_sb_offsets, size_t n_buckets_total, const unsigned int* d_bucket_ids, size_t n, void* d_dst,
+				       unsigned long long* d_result)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, d_dst);
+		if (r)
+			return r;
+		if (!d_sb_offsets || !d_bucket_ids || !d_result || bucket_bytes == 0 || (bucket_bytes & 15u) || n > 0xFFFFFFF0ull)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		cudaMemsetAsync(d_result, 0, 16, ctx->stream());
+		if (!n)
+			return 0;
+		GatherParams P;
+		P.src = (const uint8_t*)d_frame;
+		P.src_size = frame_bytes;
+		P.dst = (uint8_t*)d_dst;
+		P.total = decompressed_bytes;
+		P.bucket_bytes = (uint32_t)bucket_bytes;
+		P.n_buckets = (uint32_t)n_buckets_total;
+		P.sb_offsets = d_sb_offsets;
+		P.ids = d_bucket_ids;
+		P.n = (uint32_t)n;
+		P.result = d_result;
+		switch (T) {
+			case 2: return launch_gather_T<2>(ctx, P);
+			case 4: return launch_gather_T<4>(ctx, P);
+			case 8: return launch_gather_T<8>(ctx, P);
+		}
+		return STENOS_ERROR_INVALID_PARAMETER;
+	});
+}
+
+} // extern "C"
+
+// ---- filters --------------------------------------------------------------------------------
+namespace
+{
+	enum FilterOp { OP_SHUFFLE, OP_UNSHUFFLE, OP_DELTA, OP_DELTA_INV };
+
+	template<int T>
+	void launch_shuffle_T(stenos_context* ctx, const FilterParams& P, bool inverse)
+	{
+		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
+		const uint64_t groups = nchunks * ((P.chunk / T + 15) / 16 + 1);
+		const unsigned grid = (unsigned)((groups + FILTER_THREADS - 1) / FILTER_THREADS);
+		if (inverse)
+			STENOS_LAUNCH(unshuffle_kernel<T>, dim3(grid), dim3(FILTER_THREADS), 0, ctx->stream(), P);
+		else
+			STENOS_LAUNCH(shuffle_kernel<T>, dim3(grid), dim3(FILTER_THREADS), 0, ctx->stream(), P);
+		++g_launches;
+	}
+
+	size_t filter_impl(stenos_context* ctx, FilterOp op, size_t T, size_t bytes, size_t chunk, const void* src_, void* dst_, int with_delta)
+	{
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		if ((op == OP_SHUFFLE || op == OP_UNSHUFFLE) && !(T == 1 || supported_T(T)))
+			return STENOS_ERROR_INVALID_PARAMETER;
+		if (bytes == 0)
+			return 0;
+		if (chunk == 0 || chunk > bytes)
+			chunk = bytes;
+		const uint8_t* src = static_cast<const uint8_t*>(src_);
+		uint8_t* dst = static_cast<uint8_t*>(dst_);
+		const bool src_dev = is_device_ptr(src), dst_dev = is_device_ptr(dst);
+		cudaStream_t st = ctx->stream();
+		const uint8_t* d_src = src;
+		uint8_t* d_dst = dst;
+		if (!src_dev) {
+			if (!ctx->in.reserve(bytes + 16))
+				return STENOS_ERROR_ALLOC;
+			cudaMemcpyAsync(ctx->in.p, src, bytes, cudaMemcpyHostToDevice, st);
+			d_src = ctx->in.p;
+		}
+		if (!dst_dev) {
+			if (!ctx->out.reserve(bytes + 16))
+				return STENOS_ERROR_ALLOC;
+			d_dst = ctx->out.p;
+		}
+		FilterParams P;
+		P.src = d_src;
+		P.dst = d_dst;
+		P.bytes = bytes;
+		P.chunk = chunk;
+		P.with_delta = with_delta ? 1u : 0u;
+		const uint64_t nchunks = (bytes + chunk - 1) / chunk;
+		auto run_delta = [&](const FilterParams& Q, bool inverse) {
+			if (inverse) {
+				STENOS_LAUNCH(delta_inv_kernel, dim3((unsigned)(nchunks * 4)), dim3(FILTER_THREADS), 64, st, Q);
+			}
+			else {
+				const uint64_t groups = nchunks * ((chunk + 15) / 16);
+				STENOS_LAUNCH(delta_kernel, dim3((unsigned)((groups + FILTER_THREADS - 1) / FILTER_THREADS)), dim3(FILTER_THREADS), 0, st, Q);
+			}
+			++g_launches;
+		};
+		auto run_shuffle = [&](const FilterParams& Q, bool inverse) {
+			switch (T) {
+				case 1: cudaMemcpyAsync(Q.dst, Q.src, bytes, cudaMemcpyDeviceToDevice, st); break; // shuffle.cpp:86-87
+				case 2: launch_shuffle_T<2>(ctx, Q, inverse); break;
+				case 4: launch_shuffle_T<4>(ctx, Q, inverse); break;
+				case 8: launch_shuffle_T<8>(ctx, Q, inverse); break;
+			}
+		};
+		switch (op) {
+			case OP_SHUFFLE:
+				if (T == 1 && with_delta) {
+					run_delta(P, false);
+				}
+				else
+					run_shuffle(P, false);
+				break;
+			case OP_UNSHUFFLE:
+				if (with_delta) {
+					// delta_inv into scratch, then unshuffle (stenos.cpp:722-724)
+					if (!ctx->idx.reserve(bytes + 16))
+						return STENOS_ERROR_ALLOC;
+					FilterParams A = P;
+					A.dst = ctx->idx.p;
+					run_delta(A, true);
+					FilterParams B = P;
+					B.src = ctx->idx.p;
+					B.with_delta = 0;
+					run_shuffle(B, true);
+				}
+				else
+					run_shuffle(P, true);
+				break;
+			case OP_DELTA: run_delta(P, false); break;
+			case OP_DELTA_INV: run_delta(P, true); break;
+		}
+		if (!dst_dev) {
+			cudaMemcpyAsync(dst, d_dst, bytes, cudaMemcpyDeviceToHost, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+		}
+		return cudaGetLastError() == cudaSuccess ? bytes : STENOS_ERROR_UNDEFINED;
+	}
+}
+
+extern "C" {
+
+size_t stenos_b200_shuffle(stenos_context* ctx, size_t T, size_t bytes, size_t chunk, const void* src, void* dst, int with_delta)
+{
+	return guarded([&]() -> size_t { return filter_impl(ctx, OP_SHUFFLE, T, bytes, chunk, src, dst, with_delta); });
+}
+size_t stenos_b200_unshuffle(stenos_context* ctx, size_t T, size_t bytes, size_t chunk, const void* src, void* dst, int with_delta)
+{
+	return guarded([&]() -> size_t { return filter_impl(ctx, OP_UNSHUFFLE, T, bytes, chunk, src, dst, with_delta); });
+}
+size_t stenos_b200_delta(stenos_context* ctx, size_t bytes, size_t chunk, const void* src, void* dst)
+{
+	return guarded([&]() -> size_t { return filter_impl(ctx, OP_DELTA, 1, bytes, chunk, src, dst, 1); });
+}
+size_t stenos_b200_delta_inv(stenos_context* ctx, size_t bytes, size_t chunk, const void* src, void* dst)
+{
+	return guarded([&]() -> size_t { return filter_impl(ctx, OP_DELTA_INV, 1, bytes, chunk, src, dst, 1); });
+}
+
+size_t stenos_b200_synchronize(stenos_context* ctx)
+{
+	if (!ctx->activate())
+		return STENOS_ERROR_ALLOC;
+	if (cudaStreamSynchronize(ctx->stream()) != cudaSuccess) {
+		cudaGetLastError();
+		return STENOS_ERROR_UNDEFINED;
+	}
+	return 0;
+}
+unsigned long long stenos_b200_kernel_launches(void)
+{
+	return g_launches.load();
+}
+const char* stenos_b200_build_target(void)
+{
+#ifdef STENOS_EMU
+	return "emu";
+#else
+	return "sm_100a";
+#endif
+}
+
+} // extern "C"

@@ -1,0 +1,171 @@
+// sb_common.cuh -- shared definitions for the sm_100a level-1 stenos path.
+//
+// Format constants restate the reference's stream format (file:line relative to /root/reference):
+//   plane kinds           stenos/internal/block_compress.h:52-55
+//   block markers         stenos/internal/block_compress.h:57-60
+//   superblock codes      stenos/internal/stenos.cpp:34-39
+//   error codes           stenos/stenos.h:75-84
+#pragma once
+
+#ifdef STENOS_EMU
+#include "cuda_emu.h"
+#define STENOS_SPIN_HINT() emu::yield()
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#define STENOS_DYN_SMEM(type, name)                       \
+	extern __shared__ __align__(16) uint8_t stenos_dyn_smem_raw[]; \
+	type* name = reinterpret_cast<type*>(stenos_dyn_smem_raw)
+#define STENOS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define STENOS_SPIN_HINT() __nanosleep(20)
+#endif
+
+namespace sb
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+
+	enum : int { KIND_SAME = 0, KIND_RAW = 1, KIND_NORMAL = 2, KIND_NORMAL_RLE = 3 };
+	enum : int { MARK_COPY = 252, MARK_LZ = 253, MARK_PARTIAL = 254 };
+	enum : int { CODE_BLOCK = 1, CODE_ZSTD = 2, CODE_COPY = 6 };
+
+	constexpr uint64_t ERR_UNDEFINED = (uint64_t)-1;
+	constexpr uint64_t ERR_SRC_OVERFLOW = (uint64_t)-2;
+	constexpr uint64_t ERR_ALLOC = (uint64_t)-3;
+	constexpr uint64_t ERR_INVALID_INPUT = (uint64_t)-4;
+	constexpr uint64_t ERR_INVALID_INSTRUCTION_SET = (uint64_t)-5;
+	constexpr uint64_t ERR_DST_OVERFLOW = (uint64_t)-6;
+	constexpr uint64_t ERR_INVALID_BYTESOFTYPE = (uint64_t)-7;
+	constexpr uint64_t ERR_ZSTD_INTERNAL = (uint64_t)-8;
+	constexpr uint64_t ERR_INVALID_PARAMETER = (uint64_t)-9;
+	constexpr uint64_t LAST_ERROR_CODE = (uint64_t)-100;
+
+	constexpr uint32_t DEFAULT_SUPERBLOCK = 131072u; // STENOS_BLOCK_SIZE, stenos/stenos.h:57
+
+	// Device error bits accumulated by kernels (mapped to the codes above by the host layer)
+	enum : uint32_t { DEV_ERR_DST_OVERFLOW = 1u, DEV_ERR_SRC_OVERFLOW = 2u, DEV_ERR_INVALID_INPUT = 4u };
+
+	// ------------------------------------------------------------------------------------------
+	// byte-SIMD helpers on packed 4 x u8 words
+	// ------------------------------------------------------------------------------------------
+
+	// 0x80 in every byte of x that is zero, 0 elsewhere (exact, no cross-byte borrow)
+	__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
+	{
+		uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+		return ~(t | x | 0x7F7F7F7Fu);
+	}
+	// gathers the four 0x80 flags of z into bits 0..3
+	__device__ __forceinline__ uint32_t flags_to_mask4(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+	// replicate a byte into the four byte lanes
+	__device__ __forceinline__ uint32_t splat(uint32_t b) { return (b & 0xFFu) * 0x01010101u; }
+
+	// [hi byte 3 of `before`, bytes 0..2 of `cur`] : the word of "previous bytes" of cur
+	__device__ __forceinline__ uint32_t prev_bytes(uint32_t before, uint32_t cur) { return __byte_perm(before, cur, 0x6543); }
+
+	// inclusive prefix sum over the 4 bytes of x (mod 256 per byte)
+	__device__ __forceinline__ uint32_t prefix4(uint32_t x)
+	{
+		x = __vadd4(x, x << 8);
+		x = __vadd4(x, x << 16);
+		return x;
+	}
+
+	__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+	// 4x4 byte transpose: words a,b,c,d (one per element) -> p0..p3 (one per byte plane)
+	__device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3)
+	{
+		uint32_t t0 = __byte_perm(a, b, 0x5140); // a0 b0 a1 b1
+		uint32_t t1 = __byte_perm(c, d, 0x5140); // c0 d0 c1 d1
+		uint32_t t2 = __byte_perm(a, b, 0x7362); // a2 b2 a3 b3
+		uint32_t t3 = __byte_perm(c, d, 0x7362);
+		p0 = __byte_perm(t0, t1, 0x5410);
+		p1 = __byte_perm(t0, t1, 0x7632);
+		p2 = __byte_perm(t2, t3, 0x5410);
+		p3 = __byte_perm(t2, t3, 0x7632);
+	}
+
+	// Lane-local view of one 256-element block: lane l owns elements 8l..8l+7, i.e. for every byte
+	// plane p the 8 bytes lo[p] (elements 0..3) and hi[p] (elements 4..7).  W = 2*T input words.
+	template<int T>
+	__device__ __forceinline__ void words_to_planes(const uint32_t (&w)[2 * T], uint32_t (&lo)[T], uint32_t (&hi)[T])
+	{
+		if (T == 2) {
+			lo[0] = __byte_perm(w[0], w[1], 0x6420);
+			lo[1] = __byte_perm(w[0], w[1], 0x7531);
+			hi[0] = __byte_perm(w[2], w[3], 0x6420);
+			hi[1] = __byte_perm(w[2], w[3], 0x7531);
+		}
+		else if (T == 4) {
+			transpose4(w[0], w[1], w[2], w[3], lo[0], lo[1], lo[2], lo[3]);
+			transpose4(w[4], w[5], w[6], w[7], hi[0], hi[1], hi[2], hi[3]);
+		}
+		else { // T == 8
+			transpose4(w[0], w[2], w[4], w[6], lo[0], lo[1], lo[2], lo[3]);
+			transpose4(w[1], w[3], w[5], w[7], lo[4], lo[5], lo[6], lo[7]);
+			transpose4(w[8], w[10], w[12], w[14], hi[0], hi[1], hi[2], hi[3]);
+			transpose4(w[9], w[11], w[13], w[15], hi[4], hi[5], hi[6], hi[7]);
+		}
+	}
+	template<int T>
+	__device__ __forceinline__ void planes_to_words(const uint32_t (&lo)[T], const uint32_t (&hi)[T], uint32_t (&w)[2 * T])
+	{
+		// transpose4 is an involution on the 4x4 byte matrix
+		if (T == 2) {
+			w[0] = __byte_perm(lo[0], lo[1], 0x5140);
+			w[1] = __byte_perm(lo[0], lo[1], 0x7362);
+			w[2] = __byte_perm(hi[0], hi[1], 0x5140);
+			w[3] = __byte_perm(hi[0], hi[1], 0x7362);
+		}
+		else if (T == 4) {
+			transpose4(lo[0], lo[1], lo[2], lo[3], w[0], w[1], w[2], w[3]);
+			transpose4(hi[0], hi[1], hi[2], hi[3], w[4], w[5], w[6], w[7]);
+		}
+		else {
+			transpose4(lo[0], lo[1], lo[2], lo[3], w[0], w[2], w[4], w[6]);
+			transpose4(lo[4], lo[5], lo[6], lo[7], w[1], w[3], w[5], w[7]);
+			transpose4(hi[0], hi[1], hi[2], hi[3], w[8], w[10], w[12], w[14]);
+			transpose4(hi[4], hi[5], hi[6], hi[7], w[9], w[11], w[13], w[15]);
+		}
+	}
+
+	// 16-byte vector load/store of a lane's 8 elements (block start must be 16-byte aligned)
+	template<int T>
+	__device__ __forceinline__ void load_lane_words(const uint8_t* __restrict__ block, int lane, uint32_t (&w)[2 * T])
+	{
+		const uint4* p = reinterpret_cast<const uint4*>(block + (size_t)lane * 8 * T);
+#pragma unroll
+		for (int i = 0; i < T / 2; ++i) {
+			uint4 v = p[i];
+			w[4 * i + 0] = v.x;
+			w[4 * i + 1] = v.y;
+			w[4 * i + 2] = v.z;
+			w[4 * i + 3] = v.w;
+		}
+	}
+	template<int T>
+	__device__ __forceinline__ void store_lane_words(uint8_t* __restrict__ block, int lane, const uint32_t (&w)[2 * T])
+	{
+		uint4* p = reinterpret_cast<uint4*>(block + (size_t)lane * 8 * T);
+#pragma unroll
+		for (int i = 0; i < T / 2; ++i)
+			p[i] = make_uint4(w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+	}
+
+	// unaligned little-endian reads from a byte stream (global or shared)
+	__device__ __forceinline__ uint32_t rd16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+	__device__ __forceinline__ uint32_t rd24(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+	// reads 8 bytes at an arbitrary address through three aligned 32-bit loads
+	__device__ __forceinline__ void rd64_unaligned(const uint8_t* p, uint32_t& lo, uint32_t& hi)
+	{
+		uintptr_t a = reinterpret_cast<uintptr_t>(p);
+		const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+		uint32_t sh = (uint32_t)(a & 3) * 8;
+		uint32_t w0 = q[0], w1 = q[1];
+		uint32_t w2 = sh ? q[2] : 0u;
+		lo = __funnelshift_r(w0, w1, sh);
+		hi = __funnelshift_r(w1, w2, sh);
+	}
+}

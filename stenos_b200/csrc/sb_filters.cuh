@@ -1,0 +1,341 @@
+// sb_filters.cuh -- byte shuffle (transpose) and byte delta filters, the pre-Zstd stages of
+// levels >= 2 (stenos.cpp:513, :646, :709, :722-724).
+//
+//   shuffle      stenos::shuffle   (shuffle.cpp:82-90, semantics shuffle-generic.h:33-74)
+//   unshuffle    stenos::unshuffle (shuffle.cpp:94-102, shuffle-generic.h:83-125)
+//   delta        stenos::delta     (delta.cpp:30-71: 4 independent quarter streams when bytes > 2048)
+//   delta_inv    stenos::delta_inv (delta.cpp:230-267)
+//
+// All kernels are batched: the buffer is cut in `chunk` byte pieces (the superblock size of the
+// level: 128 KiB << shift) and every piece is filtered on its own, exactly as the reference does
+// per superblock.  Lane mapping of the transposes: a lane owns 16 consecutive elements, so every
+// byte plane receives / provides one 16-byte vector per lane and a warp moves 512 contiguous
+// elements with 128-bit accesses on both sides.
+#pragma once
+#include "sb_common.cuh"
+
+namespace sb
+{
+	struct FilterParams
+	{
+		const uint8_t* src;
+		uint8_t* dst;
+		uint64_t bytes; // total
+		uint64_t chunk; // bytes per independently filtered piece (last one may be shorter)
+		uint32_t with_delta; // shuffle: also apply the byte delta (fused); unshuffle: unused
+	};
+
+	// position i of a chunk of `bytes` bytes starts a delta stream? (delta.cpp:42-70)
+	__device__ __forceinline__ bool delta_stream_start(uint64_t i, uint64_t bytes)
+	{
+		if (i == 0)
+			return true;
+		if (bytes <= 2048)
+			return false;
+		const uint64_t q = bytes / 4;
+		return i == q || i == 2 * q || i == 3 * q;
+	}
+
+	// 16 elements of T bytes (4*T words) -> T vectors of 16 plane bytes
+	template<int T>
+	__device__ __forceinline__ void transpose16(const uint32_t (&w)[4 * T], uint4 (&pl)[T])
+	{
+		if (T == 2) {
+			uint32_t a[4], b[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				a[i] = __byte_perm(w[2 * i], w[2 * i + 1], 0x6420);
+				b[i] = __byte_perm(w[2 * i], w[2 * i + 1], 0x7531);
+			}
+			pl[0] = make_uint4(a[0], a[1], a[2], a[3]);
+			pl[1 % T] = make_uint4(b[0], b[1], b[2], b[3]);
+		}
+		else if (T == 4) {
+			uint32_t p[4][4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				transpose4(w[(4 * i) % (4 * T)], w[(4 * i + 1) % (4 * T)], w[(4 * i + 2) % (4 * T)], w[(4 * i + 3) % (4 * T)], p[0][i], p[1][i], p[2][i], p[3][i]);
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				pl[k % T] = make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
+		}
+		else {
+			uint32_t p[8][4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				transpose4(w[(8 * i) % (4 * T)], w[(8 * i + 2) % (4 * T)], w[(8 * i + 4) % (4 * T)], w[(8 * i + 6) % (4 * T)], p[0][i], p[1][i], p[2][i], p[3][i]);
+				transpose4(w[(8 * i + 1) % (4 * T)], w[(8 * i + 3) % (4 * T)], w[(8 * i + 5) % (4 * T)], w[(8 * i + 7) % (4 * T)], p[4][i], p[5][i], p[6][i], p[7][i]);
+			}
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				pl[k % T] = make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
+		}
+	}
+	template<int T>
+	__device__ __forceinline__ void untranspose16(const uint4 (&pl)[T], uint32_t (&w)[4 * T])
+	{
+		if (T == 2) {
+			const uint32_t a[4] = { pl[0].x, pl[0].y, pl[0].z, pl[0].w };
+			const uint32_t b[4] = { pl[1 % T].x, pl[1 % T].y, pl[1 % T].z, pl[1 % T].w };
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				w[(2 * i) % (4 * T)] = __byte_perm(a[i], b[i], 0x5140);
+				w[(2 * i + 1) % (4 * T)] = __byte_perm(a[i], b[i], 0x7362);
+			}
+		}
+		else if (T == 4) {
+			uint32_t p[4][4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				p[k][0] = pl[k % T].x;
+				p[k][1] = pl[k % T].y;
+				p[k][2] = pl[k % T].z;
+				p[k][3] = pl[k % T].w;
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				transpose4(p[0][i], p[1][i], p[2][i], p[3][i], w[(4 * i) % (4 * T)], w[(4 * i + 1) % (4 * T)], w[(4 * i + 2) % (4 * T)], w[(4 * i + 3) % (4 * T)]);
+		}
+		else {
+			uint32_t p[8][4];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				p[k][0] = pl[k % T].x;
+				p[k][1] = pl[k % T].y;
+				p[k][2] = pl[k % T].z;
+				p[k][3] = pl[k % T].w;
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				transpose4(p[0][i], p[1][i], p[2][i], p[3][i], w[(8 * i) % (4 * T)], w[(8 * i + 2) % (4 * T)], w[(8 * i + 4) % (4 * T)], w[(8 * i + 6) % (4 * T)]);
+				transpose4(p[4][i], p[5][i], p[6][i], p[7][i], w[(8 * i + 1) % (4 * T)], w[(8 * i + 3) % (4 * T)], w[(8 * i + 5) % (4 * T)], w[(8 * i + 7) % (4 * T)]);
+			}
+		}
+	}
+
+	// byte delta of a 16-byte vector given the byte that precedes it
+	__device__ __forceinline__ uint4 delta16(uint4 v, uint32_t before)
+	{
+		uint4 r;
+		r.x = __vsub4(v.x, prev_bytes(before << 24, v.x));
+		r.y = __vsub4(v.y, prev_bytes(v.x, v.y));
+		r.z = __vsub4(v.z, prev_bytes(v.y, v.z));
+		r.w = __vsub4(v.w, prev_bytes(v.z, v.w));
+		return r;
+	}
+	__device__ __forceinline__ void set_byte16(uint4& v, uint32_t idx, uint32_t b)
+	{
+		uint32_t* a = idx < 4 ? &v.x : idx < 8 ? &v.y : idx < 12 ? &v.z : &v.w;
+		const uint32_t sh = (idx & 3u) * 8u;
+		*a = (*a & ~(0xFFu << sh)) | (b << sh);
+	}
+
+	constexpr int FILTER_THREADS = 256;
+
+	// shuffle (+ optional fused delta).  grid.x covers groups of 16 elements of every chunk.
+	template<int T>
+	__global__ void __launch_bounds__(FILTER_THREADS) shuffle_kernel(FilterParams P)
+	{
+		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
+		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
+		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
+		const uint64_t c = g / groups_per_chunk;
+		if (c >= nchunks)
+			return;
+		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk); // bytes of this chunk
+		const uint64_t n = cb / T;                                // elements
+		const uint64_t j0 = (g - c * groups_per_chunk) * 16;      // first element of this thread
+		const uint8_t* src = P.src + c * P.chunk;
+		uint8_t* dst = P.dst + c * P.chunk;
+		if (j0 >= n) {
+			// the thread after the last group copies the leftover bytes (shuffle-generic.h:73)
+			if (j0 < n + 16) {
+				for (uint64_t i = n * T; i < cb; ++i) {
+					uint32_t b = src[i];
+					if (P.with_delta && !delta_stream_start(i, cb))
+						b = (b - src[i == n * T ? (n - 1) * T + (T - 1) : i - 1]) & 0xFFu;
+					dst[i] = (uint8_t)b;
+				}
+			}
+			return;
+		}
+		const bool vec = (j0 + 16 <= n) && ((n & 15u) == 0) && ((((uintptr_t)src) & 15u) == 0) && ((((uintptr_t)dst) & 15u) == 0);
+		if (vec) {
+			uint32_t w[4 * T];
+			const uint4* s4 = reinterpret_cast<const uint4*>(src + j0 * T);
+#pragma unroll
+			for (int i = 0; i < T; ++i) {
+				const uint4 v = s4[i];
+				w[4 * i] = v.x;
+				w[4 * i + 1] = v.y;
+				w[4 * i + 2] = v.z;
+				w[4 * i + 3] = v.w;
+			}
+			uint4 pl[T];
+			transpose16<T>(w, pl);
+#pragma unroll
+			for (int k = 0; k < T; ++k) {
+				uint4 v = pl[k];
+				if (P.with_delta) {
+					// byte before position k*n + j0 of the transposed chunk
+					const uint64_t i0 = (uint64_t)k * n + j0;
+					uint32_t before = 0;
+					if (j0)
+						before = src[(j0 - 1) * T + k];
+					else if (k)
+						before = src[(n - 1) * T + (k - 1)];
+					v = delta16(v, before);
+					// stream starts keep the raw byte
+					if (cb > 2048) {
+						const uint64_t q = cb / 4;
+#pragma unroll
+						for (int m = 0; m < 4; ++m) {
+							const uint64_t st = (uint64_t)m * q;
+							if (st >= i0 && st < i0 + 16)
+								set_byte16(v, (uint32_t)(st - i0), src[(st - (uint64_t)k * n) * T + k]);
+						}
+					}
+					else if (i0 == 0)
+						set_byte16(v, 0, src[0]);
+				}
+				*reinterpret_cast<uint4*>(dst + (uint64_t)k * n + j0) = v;
+			}
+		}
+		else {
+			// ragged / unaligned group: plain byte accesses
+			const uint64_t j1 = min(j0 + 16, n);
+			for (int k = 0; k < T; ++k)
+				for (uint64_t j = j0; j < j1; ++j) {
+					const uint64_t i = (uint64_t)k * n + j;
+					uint32_t b = src[j * T + k];
+					if (P.with_delta && !delta_stream_start(i, cb)) {
+						const uint32_t pb = j ? src[(j - 1) * T + k] : src[(n - 1) * T + (k - 1)];
+						b = (b - pb) & 0xFFu;
+					}
+					dst[i] = (uint8_t)b;
+				}
+		}
+	}
+
+	template<int T>
+	__global__ void __launch_bounds__(FILTER_THREADS) unshuffle_kernel(FilterParams P)
+	{
+		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
+		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
+		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
+		const uint64_t c = g / groups_per_chunk;
+		if (c >= nchunks)
+			return;
+		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
+		const uint64_t n = cb / T;
+		const uint64_t j0 = (g - c * groups_per_chunk) * 16;
+		const uint8_t* src = P.src + c * P.chunk;
+		uint8_t* dst = P.dst + c * P.chunk;
+		if (j0 >= n) {
+			if (j0 < n + 16)
+				for (uint64_t i = n * T; i < cb; ++i)
+					dst[i] = src[i];
+			return;
+		}
+		const bool vec = (j0 + 16 <= n) && ((n & 15u) == 0) && ((((uintptr_t)src) & 15u) == 0) && ((((uintptr_t)dst) & 15u) == 0);
+		if (vec) {
+			uint4 pl[T];
+#pragma unroll
+			for (int k = 0; k < T; ++k)
+				pl[k] = *reinterpret_cast<const uint4*>(src + (uint64_t)k * n + j0);
+			uint32_t w[4 * T];
+			untranspose16<T>(pl, w);
+			uint4* d4 = reinterpret_cast<uint4*>(dst + j0 * T);
+#pragma unroll
+			for (int i = 0; i < T; ++i)
+				d4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+		}
+		else {
+			const uint64_t j1 = min(j0 + 16, n);
+			for (uint64_t j = j0; j < j1; ++j)
+				for (int k = 0; k < T; ++k)
+					dst[j * T + k] = src[(uint64_t)k * n + j];
+		}
+	}
+
+	// plain delta (no transpose): one thread per 16 output bytes
+	__global__ void __launch_bounds__(FILTER_THREADS) delta_kernel(FilterParams P)
+	{
+		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
+		const uint64_t groups_per_chunk = (P.chunk + 15) / 16;
+		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
+		const uint64_t c = g / groups_per_chunk;
+		if (c >= nchunks)
+			return;
+		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
+		const uint64_t i0 = (g - c * groups_per_chunk) * 16;
+		if (i0 >= cb)
+			return;
+		const uint8_t* src = P.src + c * P.chunk;
+		uint8_t* dst = P.dst + c * P.chunk;
+		const uint64_t i1 = min(i0 + 16, cb);
+		for (uint64_t i = i0; i < i1; ++i)
+			dst[i] = delta_stream_start(i, cb) ? src[i] : (uint8_t)(src[i] - src[i - 1]);
+	}
+
+	// inverse delta: one CTA per (chunk, stream); the stream is scanned tile by tile with a running carry
+	__global__ void __launch_bounds__(FILTER_THREADS) delta_inv_kernel(FilterParams P)
+	{
+		STENOS_DYN_SMEM(uint32_t, warp_sums);
+		const uint64_t c = blockIdx.x >> 2;
+		const uint32_t stream = blockIdx.x & 3u;
+		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
+		uint64_t lo, hi; // byte range of this stream inside the chunk
+		if (cb > 2048) {
+			const uint64_t q = cb / 4;
+			lo = stream * q;
+			hi = stream == 3 ? cb : lo + q;
+		}
+		else {
+			if (stream)
+				return;
+			lo = 0;
+			hi = cb;
+		}
+		const uint8_t* src = P.src + c * P.chunk;
+		uint8_t* dst = P.dst + c * P.chunk;
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		uint32_t carry = 0;
+		for (uint64_t t0 = lo; t0 < hi; t0 += FILTER_THREADS * 16) {
+			const uint64_t i0 = t0 + (uint64_t)tid * 16;
+			uint8_t v[16];
+			uint32_t sum = 0;
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				v[k] = (i0 + k < hi) ? src[i0 + k] : (uint8_t)0;
+				sum += v[k];
+				v[k] = (uint8_t)sum;
+			}
+			// CTA-wide exclusive scan of the per-thread sums (mod 256)
+			uint32_t incl = sum;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				uint32_t t = __shfl_up_sync(FULL, incl, d);
+				if (lane >= d)
+					incl += t;
+			}
+			if (lane == 31)
+				warp_sums[warp] = incl;
+			__syncthreads();
+			uint32_t wpre = 0, tot = 0;
+			for (int i = 0; i < FILTER_THREADS / 32; ++i) {
+				const uint32_t ws = warp_sums[i];
+				if (i < warp)
+					wpre += ws;
+				tot += ws;
+			}
+			__syncthreads();
+			const uint32_t add = carry + wpre + (incl - sum);
+#pragma unroll
+			for (int k = 0; k < 16; ++k)
+				if (i0 + k < hi)
+					dst[i0 + k] = (uint8_t)(v[k] + add);
+			carry = (carry + tot) & 0xFFu;
+		}
+	}
+}

@@ -1,0 +1,479 @@
+// sb_kernels.cuh -- frame-level kernels of the level-1 path (device side) and their launchers.
+//
+//   encode_frame_kernel   stenos_compress_generic's superblock loop (stenos.cpp:893-904) +
+//                         compress_generic_superblock level-1 branch (:403-450, :606-615, :363-374):
+//                         persistent CTAs, one superblock at a time, every 256-element block encoded
+//                         by one warp into a shared-memory slot, in-CTA scan of the block sizes,
+//                         decoupled look-back across superblocks for the frame offsets, then one
+//                         coalesced copy-out.  HBM traffic = N (read) + C (write).
+//   frame_index_kernel    the serial walk over [code][csize:3] headers (stenos.cpp:1124-1143)
+//   decode_frame_kernel   decompress_generic_superblock codes 1 and 6 (:681-753): one warp per
+//                         superblock, blocks in sequence (the stream is not seekable)
+//   shuffle / delta       filters (see sb_filters.cuh)
+#pragma once
+#include "sb_common.cuh"
+#include "sb_encode.cuh"
+#include "sb_decode.cuh"
+
+namespace sb
+{
+	// ------------------------------------------------------------------------------------------
+	// byte copies with arbitrary alignment on both sides
+	// ------------------------------------------------------------------------------------------
+
+	// one warp copies n bytes src -> dst (dst global, src shared or global).  4-byte stores on the
+	// destination's natural alignment, bytes at both ends.
+	__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane)
+	{
+		const uint32_t head = min((uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u), n);
+		if ((uint32_t)lane < head)
+			dst[lane] = src[lane];
+		const uint32_t body = (n - head) >> 2;
+		const uint8_t* s = src + head;
+		uint32_t* d = reinterpret_cast<uint32_t*>(dst + head);
+		const uintptr_t sa = (uintptr_t)s;
+		const uint32_t sh = (uint32_t)(sa & 3u) * 8u;
+		const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+		if (sh == 0) {
+			for (uint32_t j = lane; j < body; j += 32)
+				d[j] = sw[j];
+		}
+		else {
+			for (uint32_t j = lane; j < body; j += 32)
+				d[j] = __funnelshift_r(sw[j], sw[j + 1], sh);
+		}
+		const uint32_t done = head + (body << 2);
+		if (done + (uint32_t)lane < n)
+			dst[done + lane] = src[done + lane];
+	}
+
+	// the whole CTA copies n bytes global -> global
+	__device__ __forceinline__ void cta_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int tid, int nthreads)
+	{
+		const uint32_t head = min((uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u), n);
+		if ((uint32_t)tid < head)
+			dst[tid] = src[tid];
+		const uint32_t body = (n - head) >> 4;
+		const uint8_t* s = src + head;
+		uint4* d = reinterpret_cast<uint4*>(dst + head);
+		const uintptr_t sa = (uintptr_t)s;
+		const uint32_t sh = (uint32_t)(sa & 3u) * 8u;
+		const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+		if ((sa & 15u) == 0) {
+			const uint4* s4 = reinterpret_cast<const uint4*>(s);
+			for (uint32_t j = tid; j < body; j += nthreads)
+				d[j] = s4[j];
+		}
+		else {
+			for (uint32_t j = tid; j < body; j += nthreads) {
+				const uint32_t a = sw[4 * j], b = sw[4 * j + 1], c = sw[4 * j + 2], e = sw[4 * j + 3];
+				const uint32_t f = sh ? sw[4 * j + 4] : 0u;
+				d[j] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh), __funnelshift_r(e, f, sh));
+			}
+		}
+		const uint32_t done = head + (body << 4);
+		if (done + (uint32_t)tid < n)
+			dst[done + tid] = src[done + tid];
+	}
+
+	// ------------------------------------------------------------------------------------------
+	// encoder
+	// ------------------------------------------------------------------------------------------
+	struct EncodeParams
+	{
+		const uint8_t* src;  // uncompressed input (16-byte aligned)
+		uint64_t bytes;      // bytes handled on the device (whole superblocks >= 128 bytes)
+		uint8_t* dst;        // frame output
+		uint64_t dst_size;   // capacity of dst
+		uint32_t sb_bytes;   // superblock size
+		uint32_t n_sb;       // superblocks handled by this launch
+		uint32_t header_len; // frame header bytes preceding the first superblock (8 or 12); 0 = do not write it
+		uint32_t shift_byte; // first header byte
+		uint64_t frame_bytes; // decompressed size written in the frame header (may exceed `bytes` when the host adds a Zstd tail)
+		int level;           // 0 (all COPY) or 1
+		unsigned long long* state; // [n_sb] look-back words, zero initialised
+		uint32_t* ticket;          // zero initialised
+		unsigned long long* result; // [0] offset past the last superblock written, [1] device error bits
+		unsigned long long* sb_offsets; // optional [n_sb + 1]: offset of every superblock header in dst
+		uint64_t base_offset; // offset in dst of this launch's first superblock when header_len == 0 (multi-GPU segments)
+	};
+
+	constexpr unsigned long long LB_AGGREGATE = 1ull << 62;
+	constexpr unsigned long long LB_INCLUSIVE = 2ull << 62;
+	constexpr unsigned long long LB_VALUE = (1ull << 62) - 1;
+
+	template<int T>
+	struct EncodeLayout
+	{
+		static constexpr uint32_t BLOCK = T * 256u;
+		static constexpr uint32_t HS = (T + 1) / 2;
+		static constexpr uint32_t STRIDE = (BLOCK + HS + 1u + 15u) & ~15u; // worst block / partial encoding, 16-byte aligned
+		static constexpr uint32_t MAX_BLOCKS = DEFAULT_SUPERBLOCK / BLOCK;
+		static constexpr uint32_t SLOTS_BYTES = MAX_BLOCKS * STRIDE;
+		static constexpr uint32_t NENT = MAX_BLOCKS + 1; // + partial
+		// [slots][sizes u32 x NENT][offsets u32 x (NENT+1)][misc 16 x u64][lz scratch per warp]
+		static constexpr uint32_t SIZES_OFF = SLOTS_BYTES;
+		static constexpr uint32_t OFFS_OFF = SIZES_OFF + ((NENT * 4u + 15u) & ~15u);
+		static constexpr uint32_t MISC_OFF = OFFS_OFF + (((NENT + 1) * 4u + 15u) & ~15u);
+		static constexpr uint32_t LZ_OFF = MISC_OFF + 128u;
+		static constexpr uint32_t LZ_STRIDE = (LZ_SCRATCH_BYTES + 15u) & ~15u;
+		static uint32_t smem_bytes(int nwarps) { return LZ_OFF + LZ_STRIDE * (uint32_t)nwarps; }
+	};
+
+	// worst case length of a superblock's block stream
+	template<int T>
+	__device__ __forceinline__ uint32_t worst_stream(uint32_t nfull, uint32_t rem)
+	{
+		return nfull * (T * 256u + (T + 1) / 2) + (rem ? 1u + (T + 1) / 2 + 8u * T + rem : 0u);
+	}
+
+	template<int T>
+	__global__ void __launch_bounds__(512, 1) encode_frame_kernel(EncodeParams P)
+	{
+		using L = EncodeLayout<T>;
+		STENOS_DYN_SMEM(uint8_t, smem);
+		uint32_t* sizes = reinterpret_cast<uint32_t*>(smem + L::SIZES_OFF);
+		uint32_t* offs = reinterpret_cast<uint32_t*>(smem + L::OFFS_OFF);
+		unsigned long long* misc = reinterpret_cast<unsigned long long*>(smem + L::MISC_OFF);
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		const int nwarps = blockDim.x >> 5;
+		uint32_t* lz_scratch = reinterpret_cast<uint32_t*>(smem + L::LZ_OFF + L::LZ_STRIDE * warp);
+		const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
+
+		for (;;) {
+			// ---- next superblock (ticket order == look-back order: predecessors are always running or done)
+			__syncthreads();
+			if (tid == 0)
+				misc[0] = atomicAdd(P.ticket, 1u);
+			__syncthreads();
+			const uint32_t s = (uint32_t)misc[0];
+			if (s >= P.n_sb)
+				break;
+			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
+			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
+			const uint32_t nfull = in_bytes / L::BLOCK, rem = in_bytes - nfull * L::BLOCK;
+			const uint32_t nent = nfull + (rem ? 1u : 0u);
+
+			// ---- can the reference's dst room checks change anything for this superblock?
+			// lower bound of the room: every earlier superblock stored as COPY
+			const uint32_t need = worst_stream<T>(nfull, rem) + 8u * T + 32u;
+			const long long room_lb = (long long)P.dst_size - (long long)(first_off + (uint64_t)s * (4ull + P.sb_bytes)) - 4;
+			bool have_base = false, exact = false;
+			uint64_t base = 0; // offset of this superblock's header in dst
+			long long room = room_lb;
+			if (P.level != 0 && room_lb < (long long)need) {
+				// wait for the true offset first
+				if (tid == 0) {
+					uint64_t excl = 0;
+					if (s > 0) {
+						unsigned long long v;
+						while (((v = atomicAdd(&P.state[s - 1], 0ull)) & LB_INCLUSIVE) == 0)
+							STENOS_SPIN_HINT();
+						excl = v & LB_VALUE;
+					}
+					misc[1] = first_off + excl;
+				}
+				__syncthreads();
+				base = misc[1];
+				have_base = true;
+				room = (long long)P.dst_size - (long long)base - 4;
+				exact = room < (long long)need;
+			}
+
+			bool err = false;
+			if (P.level == 0) {
+			}
+			else if (!exact) {
+				for (uint32_t b = warp; b < nfull; b += nwarps) {
+					bool e = false;
+					const uint32_t sz = encode_block<T, false>(in + (size_t)b * L::BLOCK, smem + b * L::STRIDE, lz_scratch, lane, 0xFFFFFFFFu, e);
+					if (lane == 0)
+						sizes[b] = sz;
+				}
+				if (rem && warp == (int)(nfull % nwarps)) {
+					bool e = false;
+					const uint32_t sz = encode_partial_block<T, false>(in + (size_t)nfull * L::BLOCK, rem, smem + nfull * L::STRIDE, lane, 0xFFFFFFFFu, e);
+					if (lane == 0)
+						sizes[nfull] = sz;
+				}
+			}
+			else if (warp == 0) {
+				// exact mode: the blocks of the superblock in sequence with the reference's room arithmetic
+				uint32_t off = 0;
+				for (uint32_t b = 0; b < nfull && !err; ++b) {
+					const uint32_t r = room > (long long)off ? (uint32_t)((room - (long long)off) > 0x7FFFFFFFll ? 0x7FFFFFFFll : (room - (long long)off)) : 0u;
+					const uint32_t sz = encode_block<T, true>(in + (size_t)b * L::BLOCK, smem + b * L::STRIDE, lz_scratch, lane, r, err);
+					if (lane == 0)
+						sizes[b] = sz;
+					off += sz;
+				}
+				if (rem && !err) {
+					const uint32_t r = room > (long long)off ? (uint32_t)((room - (long long)off) > 0x7FFFFFFFll ? 0x7FFFFFFFll : (room - (long long)off)) : 0u;
+					const uint32_t sz = encode_partial_block<T, true>(in + (size_t)nfull * L::BLOCK, rem, smem + nfull * L::STRIDE, lane, r, err);
+					if (lane == 0)
+						sizes[nfull] = sz;
+				}
+				if (lane == 0)
+					misc[2] = err ? 1ull : 0ull;
+			}
+			__syncthreads();
+			if (exact)
+				err = misc[2] != 0ull;
+
+			// ---- in-CTA exclusive scan of the block sizes (warp 0)
+			if (warp == 0 && P.level != 0 && !err) {
+				const uint32_t per = (nent + 31u) / 32u;
+				const uint32_t lo_i = (uint32_t)lane * per;
+				uint32_t sum = 0;
+				for (uint32_t i = lo_i; i < min(lo_i + per, nent); ++i)
+					sum += sizes[i];
+				uint32_t incl = sum;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t t = __shfl_up_sync(FULL, incl, d);
+					if (lane >= d)
+						incl += t;
+				}
+				uint32_t run = incl - sum;
+				for (uint32_t i = lo_i; i < min(lo_i + per, nent); ++i) {
+					offs[i] = run;
+					run += sizes[i];
+				}
+				if (lane == 31)
+					offs[nent] = incl;
+			}
+			__syncthreads();
+			const uint32_t csize = (P.level != 0 && !err) ? offs[nent] : 0xFFFFFFFFu;
+			const bool copy = csize > in_bytes; // stenos.cpp:609-610 (error or larger than the input -> MEMCPY)
+			const uint32_t out_size = 4u + (copy ? in_bytes : csize);
+
+			// ---- frame offset: publish, look back
+			if (tid == 0) {
+				uint64_t excl;
+				if (have_base)
+					excl = base - first_off;
+				else {
+					atomicExch(&P.state[s], LB_AGGREGATE | (unsigned long long)out_size);
+					excl = 0;
+					for (long long j = (long long)s - 1; j >= 0;) {
+						const unsigned long long v = atomicAdd(&P.state[j], 0ull);
+						if (v & LB_INCLUSIVE) {
+							excl += v & LB_VALUE;
+							break;
+						}
+						if (v & LB_AGGREGATE) {
+							excl += v & LB_VALUE;
+							--j;
+							continue;
+						}
+						STENOS_SPIN_HINT();
+					}
+				}
+				atomicExch(&P.state[s], LB_INCLUSIVE | (unsigned long long)(excl + out_size));
+				misc[1] = first_off + excl;
+				if (P.sb_offsets) {
+					P.sb_offsets[s] = first_off + excl;
+					if (s == P.n_sb - 1)
+						P.sb_offsets[s + 1] = first_off + excl + out_size;
+				}
+				if (s == P.n_sb - 1)
+					P.result[0] = first_off + excl + out_size;
+			}
+			__syncthreads();
+			base = misc[1];
+			if (base + out_size > P.dst_size) {
+				// stenos.cpp:366-367 / :611-612: the caller's buffer is too small
+				if (tid == 0)
+					atomicOr(&P.result[1], (unsigned long long)DEV_ERR_DST_OVERFLOW);
+				continue;
+			}
+
+			// ---- copy out: [code][csize:3] + payload
+			uint8_t* out = P.dst + base;
+			if (tid == 0) {
+				const uint32_t len = copy ? in_bytes : csize;
+				out[0] = (uint8_t)(copy ? CODE_COPY : CODE_BLOCK);
+				out[1] = (uint8_t)len;
+				out[2] = (uint8_t)(len >> 8);
+				out[3] = (uint8_t)(len >> 16);
+				if (s == 0 && P.header_len) {
+					// frame header (stenos.cpp:862-874): [shift][decompressed bytes:7]([superblock bytes:4])
+					P.dst[0] = (uint8_t)P.shift_byte;
+					for (int i = 0; i < 7; ++i)
+						P.dst[1 + i] = (uint8_t)(P.frame_bytes >> (8 * i));
+					if (P.header_len == 12)
+						for (int i = 0; i < 4; ++i)
+							P.dst[8 + i] = (uint8_t)(P.sb_bytes >> (8 * i));
+				}
+			}
+			if (copy)
+				cta_copy_bytes(out + 4, in, in_bytes, tid, blockDim.x);
+			else
+				for (uint32_t b = warp; b < nent; b += nwarps)
+					warp_copy_bytes(out + 4 + offs[b], smem + b * L::STRIDE, sizes[b], lane);
+		}
+	}
+
+	// ------------------------------------------------------------------------------------------
+	// frame index: offsets of the superblock headers of a frame that lives in device memory
+	// ------------------------------------------------------------------------------------------
+	struct IndexParams
+	{
+		const uint8_t* src;
+		uint64_t src_size;
+		uint64_t first;  // offset of the first superblock header
+		uint32_t n_sb;
+		unsigned long long* sb_offsets; // [n_sb + 1]
+		unsigned long long* result;     // [1] error bits
+	};
+
+	__global__ void frame_index_kernel(IndexParams P)
+	{
+		if (threadIdx.x != 0 || blockIdx.x != 0)
+			return;
+		uint64_t at = P.first;
+		for (uint32_t i = 0; i < P.n_sb; ++i) {
+			P.sb_offsets[i] = at;
+			if (at + 4 > P.src_size) {
+				atomicOr(&P.result[1], (unsigned long long)DEV_ERR_SRC_OVERFLOW);
+				for (uint32_t j = i; j <= P.n_sb; ++j)
+					P.sb_offsets[j] = P.src_size;
+				return;
+			}
+			at += 4ull + rd24(P.src + at + 1);
+		}
+		P.sb_offsets[P.n_sb] = at;
+		if (at > P.src_size)
+			atomicOr(&P.result[1], (unsigned long long)DEV_ERR_INVALID_INPUT);
+	}
+
+	// ------------------------------------------------------------------------------------------
+	// decoder: one warp per superblock
+	// ------------------------------------------------------------------------------------------
+	struct DecodeParams
+	{
+		const uint8_t* src;
+		uint64_t src_size;
+		uint8_t* dst;        // 16-byte aligned
+		uint64_t total;      // decompressed bytes of the frame
+		uint32_t sb_bytes;
+		uint32_t n_sb;
+		uint32_t first_sb;   // superblocks [first_sb, first_sb + n_sb) are decoded by this launch
+		const unsigned long long* sb_offsets; // [>= first_sb + n_sb + 1] offsets of superblock headers in src
+		unsigned long long* result;           // [1] error bits
+		uint32_t skip_zstd_tail;              // 1: a code-2 (Zstd) final superblock is left to the host
+		uint64_t dst_origin; // decompressed offset that dst[0] corresponds to (multi-GPU segments)
+	};
+
+	constexpr int DECODE_WARPS = 4;
+
+	// One warp decodes one superblock [code][csize:3][payload] found at offset `at` of src into
+	// dsize bytes at `out` (16-byte aligned).  Returns 0 or device error bits.
+	template<int T>
+	__device__ __forceinline__ uint32_t decode_superblock_warp(const uint8_t* src, uint64_t src_size, uint64_t at, uint32_t dsize, uint8_t* out, uint16_t* lz_scratch,
+								   int lane, bool allow_zstd_tail)
+	{
+		const uint8_t* lim = src + src_size;
+		if (at + 4 > src_size)
+			return DEV_ERR_SRC_OVERFLOW; // stenos.cpp:1126-1127
+		const uint8_t* p = src + at;
+		const uint32_t code = p[0], csize = rd24(p + 1);
+		const uint8_t* q = p + 4;
+		const uint8_t* end = q + csize;
+		if (at + 4 + csize > src_size)
+			return DEV_ERR_INVALID_INPUT; // stenos.cpp:1133-1134
+		if (code == (uint32_t)CODE_COPY) {
+			if (csize != dsize)
+				return DEV_ERR_INVALID_INPUT; // stenos.cpp:743-744
+			// aligned destination, arbitrary source
+			const uint32_t nw = dsize >> 2;
+			uint32_t* d = reinterpret_cast<uint32_t*>(out);
+			const uintptr_t sa = (uintptr_t)q;
+			const uint32_t sh = (uint32_t)(sa & 3u) * 8u;
+			const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+			for (uint32_t j = lane; j < nw; j += 32)
+				d[j] = sh ? __funnelshift_r(sw[j], sw[j + 1], sh) : sw[j];
+			for (uint32_t j = (nw << 2) + lane; j < dsize; j += 32)
+				out[j] = q[j];
+			return 0;
+		}
+		if (code == (uint32_t)CODE_BLOCK) {
+			constexpr uint32_t BLOCK = T * 256u;
+			const uint32_t nfull = dsize / BLOCK, rem = dsize - nfull * BLOCK;
+			if (csize == 0 && dsize)
+				return DEV_ERR_INVALID_INPUT;
+			for (uint32_t b = 0; b < nfull; ++b) {
+				const uint32_t r = decode_block<T>(q, end, lim, out + (size_t)b * BLOCK, lz_scratch, lane);
+				if (r == 0xFFFFFFFFu)
+					return DEV_ERR_INVALID_INPUT;
+				q += r;
+			}
+			if (rem) {
+				if (q >= end || *q != (uint8_t)MARK_PARTIAL) // block_compress.h:2160-2166
+					return DEV_ERR_INVALID_INPUT;
+				const uint32_t r = decode_partial_block<T>(q + 1, end, lim, out + (size_t)nfull * BLOCK, rem, lane);
+				if (r == 0xFFFFFFFFu)
+					return DEV_ERR_INVALID_INPUT;
+			}
+			return 0;
+		}
+		if (code == (uint32_t)CODE_ZSTD && allow_zstd_tail && dsize < 128u)
+			return 0; // tiny final superblock (stenos.cpp:435-437): decoded by the host layer through libzstd
+		return DEV_ERR_INVALID_INPUT; // codes 3,4,5 carry Zstd payloads (levels >= 2): out of scope
+	}
+
+	template<int T>
+	__global__ void __launch_bounds__(DECODE_WARPS * 32) decode_frame_kernel(DecodeParams P)
+	{
+		STENOS_DYN_SMEM(uint8_t, smem);
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		uint16_t* lz_scratch = reinterpret_cast<uint16_t*>(smem) + 256 * warp;
+		const uint32_t i = blockIdx.x * DECODE_WARPS + warp;
+		if (i >= P.n_sb)
+			return;
+		const uint32_t s = P.first_sb + i;
+		const uint64_t doff = (uint64_t)s * P.sb_bytes;
+		const uint32_t dsize = (uint32_t)min((uint64_t)P.sb_bytes, P.total - doff); // remainder 0 = full superblock (appendix C1)
+		const bool last = (doff + dsize == P.total);
+		const uint32_t bad = decode_superblock_warp<T>(P.src, P.src_size, P.sb_offsets[s], dsize, P.dst + (doff - P.dst_origin), lz_scratch, lane, P.skip_zstd_tail && last);
+		if (bad && lane == 0)
+			atomicOr(&P.result[1], (unsigned long long)bad);
+	}
+
+	// stenos::cvector random access: one warp per requested bucket (cvector.hpp:2879 -> :1862-1883)
+	struct GatherParams
+	{
+		const uint8_t* src;
+		uint64_t src_size;
+		uint8_t* dst;          // [n x bucket_bytes]
+		uint64_t total;        // decompressed bytes of the whole container
+		uint32_t bucket_bytes; // superblock size of the frame
+		uint32_t n_buckets;
+		const unsigned long long* sb_offsets;
+		const uint32_t* ids;
+		uint32_t n;
+		unsigned long long* result;
+	};
+
+	template<int T>
+	__global__ void __launch_bounds__(DECODE_WARPS * 32) gather_decode_kernel(GatherParams P)
+	{
+		STENOS_DYN_SMEM(uint8_t, smem);
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		uint16_t* lz_scratch = reinterpret_cast<uint16_t*>(smem) + 256 * warp;
+		const uint32_t i = blockIdx.x * DECODE_WARPS + warp;
+		if (i >= P.n)
+			return;
+		const uint32_t id = P.ids[i];
+		uint32_t bad;
+		if (id >= P.n_buckets)
+			bad = DEV_ERR_INVALID_INPUT;
+		else {
+			const uint64_t doff = (uint64_t)id * P.bucket_bytes;
+			const uint32_t dsize = (uint32_t)min((uint64_t)P.bucket_bytes, P.total - doff);
+			bad = decode_superblock_warp<T>(P.src, P.src_size, P.sb_offsets[id], dsize, P.dst + (uint64_t)i * P.bucket_bytes, lz_scratch, lane, false);
+		}
+		if (bad && lane == 0)
+			atomicOr(&P.result[1], (unsigned long long)bad);
+	}
+}

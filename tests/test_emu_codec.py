@@ -1,0 +1,146 @@
+"""CPU-only: the product's CUDA sources compiled against the SIMT emulator (tests/emu) and checked
+bit-for-bit against the oracle.  This is a unit test of kernel + host logic on a machine without a
+GPU -- NOT a product code path (the product library is the nvcc build, see test_capi.py)."""
+import numpy as np
+import pytest
+
+import dists
+import emu_lib
+from oracle import port
+from stenos_b200 import api, capi
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated_library():
+    prev = capi._LIB
+    emu_lib.activate()
+    yield
+    capi.use_library(prev)
+
+
+def raw_of(a):
+    return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+def run(fn, *a, **k):
+    try:
+        return fn(*a, **k)
+    except api.StenosError as e:
+        return e.name
+    except RuntimeError as e:
+        return {"-6": "DST_OVERFLOW", "-2": "SRC_OVERFLOW", "-4": "INVALID_INPUT"}.get(str(e).split()[-1], str(e))
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_frames_match_oracle(T):
+    for name in dists.names():
+        for n in (256, 700, 33):
+            raw = raw_of(dists.make(name, n, T, seed=5))
+            want = port.compress(raw, T)
+            assert api.compress(raw, T) == want, (name, n)
+            assert api.decompress(want, T, raw.size) == raw.tobytes(), (name, n)
+
+
+def test_multi_superblock_frame_and_index():
+    for T, name in ((4, "ramp_noise16"), (8, "lz_then_noise"), (2, "smooth_sine")):
+        n = (131072 * 2 + 5000) // T
+        raw = raw_of(dists.make(name, n, T, seed=9))
+        want = port.compress(raw, T)
+        got = api.compress(raw, T)
+        assert got == want
+        assert api.decompress(got, T, raw.size) == raw.tobytes()
+
+
+def test_exact_multiple_of_superblock_roundtrip():
+    raw = raw_of(dists.make("sorted", 32768, 4))
+    c = api.compress(raw, 4)
+    assert c == port.compress(raw, 4)
+    assert api.decompress(c, 4, raw.size) == raw.tobytes()  # the reference decoder fails here (appendix C1)
+
+
+def test_tiny_and_empty_inputs():
+    ctx = api.Context()
+    assert ctx.compress(b"", 4) == port.compress(np.zeros(0, np.uint8), 4)
+    assert ctx.decompress(port.compress(np.zeros(0, np.uint8), 4), 4, 0) == b""
+    for n in (1, 7, 31, 32, 33, 63):  # < 128 bytes: Zstd / COPY superblock through libzstd
+        raw = raw_of(dists.make("ramp_noise4", n, 4, seed=n))[: 4 * n]
+        want = port.compress(raw, 4)
+        assert ctx.compress(raw, 4) == want
+        assert ctx.decompress(want, 4, raw.size) == raw.tobytes()
+    raw = raw_of(dists.make("sorted", 8192 + 10, 4))  # full superblock + 40 byte tail
+    want = port.compress(raw, 4)
+    assert ctx.compress(raw, 4) == want
+    assert ctx.decompress(want, 4, raw.size) == raw.tobytes()
+
+
+def test_level0_and_unsupported_parameters():
+    raw = raw_of(dists.make("sorted", 40000, 4))
+    assert api.compress(raw, 4, level=0) == port.compress(raw, 4, level=0)
+    assert api.decompress(port.compress(raw, 4, level=0), 4, raw.size) == raw.tobytes()
+    assert run(api.compress, raw, 4, level=2) == "INVALID_PARAMETER"  # Zstd levels: no CPU fallback
+    assert run(api.compress, raw[:39999], 3) == "INVALID_PARAMETER"
+    assert run(api.compress, raw, 0) == "INVALID_BYTESOFTYPE"
+    ctx = api.Context()
+    ctx.set_max_nanoseconds(1000)
+    assert run(ctx.compress, raw, 4) == "INVALID_PARAMETER"
+
+
+def test_room_dependent_decisions():
+    ctx = api.Context()
+    for T in (4, 8):
+        for name in ("random", "lz_pairs", "repeat_period7", "sorted", "mostly_random_some_repeats"):
+            raw = raw_of(dists.make(name, 256, T, seed=1))
+            for room in (T * 256 + 16, T * 256 + 4, T * 256 + 64, T * 256 + 300):
+                w = run(port.compress_superblock, raw, T, room=room)
+                assert run(ctx.compress_block, raw, T, room=room) == w, (T, name, room)
+                if isinstance(w, bytes):
+                    assert ctx.decompress_block(w, T, raw.size) == raw.tobytes()
+            raw = raw_of(dists.make(name, 3000, T, seed=2))
+            full = len(port.compress(raw, T))
+            for ds in (full + 8, full, full - 1, raw.size, 20, 7):
+                assert run(ctx.compress, raw, T, dst_size=ds) == run(port.compress, raw, T, dst_size=ds), (T, name, ds)
+
+
+def test_cvector_style_frame():
+    # custom superblock = one 256 element block per bucket, 12 byte header (cvector.hpp:3034-3093)
+    ctx = api.Context(block_shift=0)
+    raw = raw_of(dists.make("sparse_changes", 256 * 9 + 100, 4, seed=3))
+    want = port.compress(raw, 4, block_shift=0)
+    assert ctx.compress(raw, 4) == want
+    assert api.decompress(want, 4, raw.size) == raw.tobytes()
+
+
+def test_corrupt_input_is_rejected_not_overrun():
+    raw = raw_of(dists.make("ramp_noise16", 3000, 4, seed=4))
+    c = bytearray(port.compress(raw, 4))
+    assert run(api.decompress, bytes(c[: len(c) // 2]), 4, raw.size) in ("SRC_OVERFLOW", "INVALID_INPUT")
+    c2 = bytearray(c)
+    c2[8] = 9  # unknown superblock code
+    assert run(api.decompress, bytes(c2), 4, raw.size) == "INVALID_INPUT"
+    assert run(api.decompress, bytes(c), 4, raw.size - 1) == "DST_OVERFLOW"
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        c3 = bytearray(c)
+        for k in rng.integers(12, len(c), 4):
+            c3[k] ^= int(rng.integers(1, 256))
+        r = run(api.decompress, bytes(c3), 4, raw.size)  # must return (anything) without crashing
+        assert isinstance(r, (bytes, str))
+
+
+def test_filters_match_oracle():
+    ctx = api.Context()
+    rng = np.random.default_rng(3)
+    for T in (2, 4, 8):
+        for n in (0, 1, 100, 2048 // T + 1, 5000, 16384):
+            a = rng.integers(0, 256, n * T + (int(rng.integers(0, T)) if n else 0), dtype=np.uint8)
+            for chunk in (0, 4096):
+                step = chunk or max(a.size, 1)
+                pieces = [a[i:i + step] for i in range(0, a.size, step)]
+                sh = b"".join(port.shuffle(p, T) for p in pieces)
+                shd = b"".join(port.delta(np.frombuffer(port.shuffle(p, T), dtype=np.uint8)) for p in pieces)
+                assert ctx.shuffle(a, T, chunk) == sh
+                assert ctx.shuffle(a, T, chunk, True) == shd
+                assert ctx.unshuffle(np.frombuffer(sh, dtype=np.uint8), T, chunk) == a.tobytes()
+                assert ctx.unshuffle(np.frombuffer(shd, dtype=np.uint8), T, chunk, True) == a.tobytes()
+            assert ctx.delta(a) == port.delta(a)
+            assert ctx.delta_inv(np.frombuffer(port.delta(a), dtype=np.uint8)) == a.tobytes()
