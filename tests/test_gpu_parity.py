@@ -1,0 +1,264 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI of
+libstenos_b200.so, against the CPU oracle on the same seeded inputs, against the committed golden
+vectors of the reference, and -- at BASELINE.json sizes -- through size independent properties.
+Bar: bit exact (integer / byte work)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dists
+from oracle import port
+from stenos_b200 import api, capi, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def native_library():
+    # the nvcc build, never the emulator: fail loudly if it is missing
+    capi.use_library(capi.load())
+    assert capi.lib().stenos_b200_build_target() == b"sm_100a"
+    yield
+
+
+def raw_of(a):
+    return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def run(fn, *a, **k):
+    try:
+        return fn(*a, **k)
+    except api.StenosError as e:
+        return e.name
+    except RuntimeError as e:
+        return {"-6": "DST_OVERFLOW", "-2": "SRC_OVERFLOW", "-4": "INVALID_INPUT"}.get(str(e).split()[-1], str(e))
+
+
+def test_readme_example_known_answer():
+    a = np.arange(1000000, dtype=np.int32)
+    c = api.compress(a, 4)
+    assert len(c) == 70464
+    assert c[:24].hex() == "0000093d000000000100090003008988888888888888fdff"
+    assert api.decompress(c, 4, a.nbytes) == a.tobytes()
+
+
+def test_golden_small_streams():
+    z = np.load(os.path.join(GOLD, "small.npz"))
+    keys = sorted(k[:-3] for k in z.files if k.endswith("_in"))
+    ctx = api.Context()
+    for k in keys:
+        raw, want = z[k + "_in"], z[k + "_out"].tobytes()
+        if k.startswith("bucket"):
+            T = int(k.split("_")[1][1:])
+            assert ctx.compress_block(raw, T, room=T * 256 + 16) == want, k
+            assert ctx.decompress_block(want, T, raw.size) == raw.tobytes(), k
+        else:
+            T = int(k.split("_")[0][1:])
+            assert ctx.compress(raw, T) == want, k
+            assert ctx.decompress(want, T, raw.size) == raw.tobytes(), k
+
+
+def test_golden_large_streams():
+    with open(os.path.join(GOLD, "large.json")) as f:
+        cases = json.load(f)
+    ctx = api.Context()
+    n = 0
+    for c in cases:
+        if c["kind"] == "filter":
+            continue
+        raw = raw_of(dists.make(c["name"], c["n"], c["T"], seed=c["seed"]) if c["kind"] == "dists" else synth.make(c["name"], c["n"]))
+        assert sha(raw) == c["in_sha256"]
+        got = ctx.compress(raw, c["T"])
+        assert len(got) == c["out_len"] and sha(got) == c["out_sha256"], c
+        assert ctx.decompress(got, c["T"], raw.size) == raw.tobytes()
+        n += 1
+    assert n >= 60
+
+
+def test_golden_filters():
+    z = np.load(os.path.join(GOLD, "filters.npz"))
+    ctx = api.Context()
+    for k in sorted(k[:-3] for k in z.files if k.endswith("_in")):
+        T = int(k.split("_")[0][1:])
+        a = z[k + "_in"]
+        assert ctx.shuffle(a, T) == z[k + "_shuffle"].tobytes(), k
+        assert ctx.shuffle(a, T, 0, True) == z[k + "_shuffle_delta"].tobytes(), k
+        assert ctx.unshuffle(z[k + "_shuffle"], T) == a.tobytes(), k
+        assert ctx.unshuffle(z[k + "_shuffle_delta"], T, 0, True) == a.tobytes(), k
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_fuzz_vs_oracle(T):
+    ctx = api.Context()
+    for name in dists.names():
+        for n in (256, 256 * 7 + 13, 131072 // T + 100, 33, (5 * 131072) // T + 999):
+            raw = raw_of(dists.make(name, n, T, seed=n + 1))
+            want = port.compress(raw, T)
+            assert ctx.compress(raw, T) == want, (name, n)
+            assert ctx.decompress(want, T, raw.size) == raw.tobytes(), (name, n)
+
+
+def test_edge_cases():
+    ctx = api.Context()
+    assert ctx.compress(b"", 4) == port.compress(np.zeros(0, np.uint8), 4)
+    assert ctx.decompress(ctx.compress(b"", 4), 4, 0) == b""
+    for n in (1, 31, 32, 33, 63):  # tail superblock < 128 bytes -> Zstd or COPY
+        raw = raw_of(dists.make("ramp_noise4", n, 4, seed=n))
+        want = port.compress(raw, 4)
+        assert ctx.compress(raw, 4) == want
+        assert ctx.decompress(want, 4, raw.size) == raw.tobytes()
+    raw = raw_of(dists.make("sorted", 2 * 32768, 4))  # exact multiple of the superblock (reference decoder bug C1)
+    c = ctx.compress(raw, 4)
+    assert c == port.compress(raw, 4) and ctx.decompress(c, 4, raw.size) == raw.tobytes()
+    raw = raw_of(dists.make("random", 40000, 8, seed=1))  # incompressible -> COPY superblocks
+    c = ctx.compress(raw, 8)
+    assert c == port.compress(raw, 8) and ctx.decompress(c, 8, raw.size) == raw.tobytes()
+    assert api.compress(raw, 8, level=0) == port.compress(raw, 8, level=0)
+    assert run(api.compress, raw, 8, level=3) == "INVALID_PARAMETER"
+    assert run(api.compress, raw[:39999], 3) == "INVALID_PARAMETER"
+
+
+def test_room_dependent_decisions():
+    ctx = api.Context()
+    for T in (2, 4, 8):
+        for name in dists.names():
+            raw = raw_of(dists.make(name, 256, T, seed=1))
+            for room in (T * 256 + 16, T * 256 + 4, T * 256 + 64):
+                assert run(ctx.compress_block, raw, T, room=room) == run(port.compress_superblock, raw, T, room=room), (T, name, room)
+            raw = raw_of(dists.make(name, 3000, T, seed=2))
+            full = len(port.compress(raw, T))
+            for ds in (full + 40, full, full - 1, raw.size, 20, 7):
+                assert run(ctx.compress, raw, T, dst_size=ds) == run(port.compress, raw, T, dst_size=ds), (T, name, ds)
+
+
+def test_corrupt_streams_are_rejected():
+    ctx = api.Context()
+    raw = raw_of(dists.make("ramp_noise16", 50000, 4, seed=4))
+    c = bytearray(port.compress(raw, 4))
+    assert run(ctx.decompress, bytes(c[: len(c) // 2]), 4, raw.size) in ("SRC_OVERFLOW", "INVALID_INPUT")
+    assert run(ctx.decompress, bytes(c), 4, raw.size - 1) == "DST_OVERFLOW"
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        c3 = bytearray(c)
+        for k in rng.integers(8, len(c), 6):
+            c3[k] ^= int(rng.integers(1, 256))
+        assert isinstance(run(ctx.decompress, bytes(c3), 4, raw.size), (bytes, str))
+    assert ctx.decompress(bytes(c), 4, raw.size) == raw.tobytes()  # the context is still healthy
+
+
+def test_filters_vs_oracle_with_chunks():
+    ctx = api.Context()
+    for wl, T in (("float64_sensor", 8), ("float32_sensor", 4), ("int16_sine", 2)):
+        a = raw_of(synth.make(wl, (1 << 20) // T + 3))
+        for chunk in (131072, 262144, 524288):
+            pieces = [a[i:i + chunk] for i in range(0, a.size, chunk)]
+            sh = b"".join(port.shuffle(p, T) for p in pieces)
+            shd = b"".join(port.delta(np.frombuffer(port.shuffle(p, T), dtype=np.uint8)) for p in pieces)
+            assert ctx.shuffle(a, T, chunk) == sh
+            assert ctx.shuffle(a, T, chunk, True) == shd
+            assert ctx.unshuffle(np.frombuffer(sh, dtype=np.uint8), T, chunk) == a.tobytes()
+            assert ctx.unshuffle(np.frombuffer(shd, dtype=np.uint8), T, chunk, True) == a.tobytes()
+            assert ctx.delta(a, chunk) == b"".join(port.delta(p) for p in pieces)
+
+
+def test_device_resident_async_api_and_index():
+    import torch
+
+    dev = torch.device("cuda:0")
+    a = synth.make("int32_ramp_runs", 1 << 22)
+    want = port.compress(a, 4)
+    ctx = api.Context(stream=torch.cuda.current_stream())
+    d_src = torch.from_numpy(raw_of(a).copy()).to(dev)
+    cap = api.bound(a.nbytes)
+    d_dst = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    n_sb = (a.nbytes + 131071) // 131072
+    d_off = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
+    ctx.compress_async(d_src, 4, a.nbytes, d_dst, cap, d_res, d_off)
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy()
+    assert res[1] == 0 and res[0] == len(want)
+    assert d_dst[: len(want)].cpu().numpy().tobytes() == want
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), port.frame_index(want, 4))
+    # decode with the index produced by the encoder, and with the on-device header walk
+    for offs in (d_off, None):
+        d_out = torch.zeros(a.nbytes, dtype=torch.uint8, device=dev)
+        ctx.decompress_async(d_dst, 4, len(want), d_out, a.nbytes, a.nbytes, d_res, offs)
+        torch.cuda.synchronize()
+        assert d_res.cpu().numpy()[1] == 0
+        assert d_out.cpu().numpy().tobytes() == a.tobytes()
+    # frame index of a foreign (oracle produced) frame
+    d_f = torch.from_numpy(np.frombuffer(want, dtype=np.uint8).copy()).to(dev)
+    d_off2 = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
+    assert ctx.frame_index_async(d_f, len(want), 4, d_off2, n_sb + 1, d_res) == n_sb
+    torch.cuda.synchronize()
+    assert np.array_equal(d_off2.cpu().numpy().astype(np.uint64), port.frame_index(want, 4))
+
+
+def test_cvector_bucket_gather():
+    import torch
+
+    dev = torch.device("cuda:0")
+    n_buckets = 4096
+    a = synth.make("int32_ramp_runs", n_buckets * 256)
+    frame = port.compress(a, 4, block_shift=0)  # what cvector<int>::serialize() produces (12 byte header, 1 KiB buckets)
+    ctx = api.Context(stream=torch.cuda.current_stream(), block_shift=0)
+    assert ctx.compress(a, 4) == frame
+    d_f = torch.from_numpy(np.frombuffer(frame, dtype=np.uint8).copy()).to(dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    d_off = torch.zeros(n_buckets + 1, dtype=torch.int64, device=dev)
+    assert ctx.frame_index_async(d_f, len(frame), 4, d_off, n_buckets + 1, d_res) == n_buckets
+    rng = np.random.default_rng(1)
+    ids = rng.integers(0, n_buckets, 10000).astype(np.uint32)
+    d_ids = torch.from_numpy(ids.view(np.int32).copy()).to(dev)
+    d_out = torch.zeros(ids.size * 1024, dtype=torch.uint8, device=dev)
+    ctx.gather_decode_async(d_f, len(frame), 4, 1024, a.nbytes, d_off, n_buckets, d_ids, ids.size, d_out, d_res)
+    torch.cuda.synchronize()
+    assert d_res.cpu().numpy()[1] == 0
+    got = d_out.cpu().numpy().view(np.int32).reshape(-1, 256)
+    assert np.array_equal(got, a.reshape(-1, 256)[ids])
+
+
+def test_full_size_roundtrip_properties():
+    """BASELINE.json config 2 at full size (1 GiB int32): device resident round trip; the stream is
+    checked against the oracle on sampled superblocks (superblocks are independent) and through a
+    checksum of the decoded output."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    n = 1 << 28
+    a = synth.make("int32_ramp_runs", n)
+    ctx = api.Context(stream=torch.cuda.current_stream())
+    d_src = torch.from_numpy(raw_of(a)).to(dev)
+    cap = api.bound(a.nbytes)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    n_sb = a.nbytes // 131072
+    d_off = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
+    ctx.compress_async(d_src, 4, a.nbytes, d_dst, cap, d_res, d_off)
+    torch.cuda.synchronize()
+    total, err = (int(x) for x in d_res.cpu().numpy())
+    assert err == 0
+    offs = d_off.cpu().numpy()
+    assert offs[0] == 8 and offs[-1] == total and np.all(np.diff(offs) > 4)
+    head = d_dst[:8].cpu().numpy().tobytes()
+    assert head == bytes([0]) + int(a.nbytes).to_bytes(7, "little")
+    rng = np.random.default_rng(7)
+    for s in [0, 1, n_sb - 1] + list(rng.integers(0, n_sb, 24)):
+        s = int(s)
+        got = d_dst[int(offs[s]): int(offs[s + 1])].cpu().numpy().tobytes()
+        want = port.compress_superblock(a[s * 32768: (s + 1) * 32768], 4, room=1 << 20)
+        assert got == want, s
+    d_out = torch.empty(a.nbytes, dtype=torch.uint8, device=dev)
+    ctx.decompress_async(d_dst, 4, total, d_out, a.nbytes, a.nbytes, d_res, d_off)
+    torch.cuda.synchronize()
+    assert d_res.cpu().numpy()[1] == 0
+    assert torch.equal(d_out, d_src)
