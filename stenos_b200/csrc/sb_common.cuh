@@ -49,6 +49,19 @@ namespace sb
 	// byte-SIMD helpers on packed 4 x u8 words
 	// ------------------------------------------------------------------------------------------
 
+	// PTX prmt.b32 in its default mode: selector nibble bit 3 replicates the SIGN of the selected byte.
+	// (__byte_perm masks the selector with 0x7777, so it cannot express sign replication.)
+	__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
+	{
+#ifdef STENOS_EMU
+		return emu::prmt_b32(a, b, sel);
+#else
+		uint32_t r;
+		asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+		return r;
+#endif
+	}
+
 	// 0x80 in every byte of x that is zero, 0 elsewhere (exact, no cross-byte borrow)
 	__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
 	{

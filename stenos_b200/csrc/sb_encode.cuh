@@ -18,10 +18,10 @@ namespace sb
 	// signed min / max of the 8 bytes (lo,hi) as s16x2 pairs (two partial results per register)
 	__device__ __forceinline__ void minmax8_s16x2(uint32_t lo, uint32_t hi, uint32_t& mn, uint32_t& mx)
 	{
-		uint32_t a0 = __byte_perm(lo, 0, 0x9180); // sign-extended bytes 0,1
-		uint32_t a1 = __byte_perm(lo, 0, 0xB3A2); // bytes 2,3
-		uint32_t a2 = __byte_perm(hi, 0, 0x9180);
-		uint32_t a3 = __byte_perm(hi, 0, 0xB3A2);
+		uint32_t a0 = prmt_sx(lo, 0, 0x9180); // sign-extended bytes 0,1
+		uint32_t a1 = prmt_sx(lo, 0, 0xB3A2); // bytes 2,3
+		uint32_t a2 = prmt_sx(hi, 0, 0x9180);
+		uint32_t a3 = prmt_sx(hi, 0, 0xB3A2);
 		mn = __vmins2(__vimin3_s16x2(a0, a1, a2), a3);
 		mx = __vmaxs2(__vimax3_s16x2(a0, a1, a2), a3);
 	}

@@ -395,19 +395,25 @@ static inline unsigned __match_any_sync(unsigned, unsigned v)
 // ---------------------------------------------------------------------------------------------
 // Integer intrinsics
 // ---------------------------------------------------------------------------------------------
-static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
+namespace emu
 {
-	uint64_t t = ((uint64_t)b << 32) | a;
-	unsigned r = 0;
-	for (int i = 0; i < 4; ++i) {
-		unsigned sel = (s >> (4 * i)) & 0xF;
-		unsigned byte = (unsigned)(t >> (8 * (sel & 7))) & 0xFF;
-		if (sel & 8)
-			byte = (byte & 0x80) ? 0xFF : 0x00;
-		r |= byte << (8 * i);
+	// PTX prmt.b32, default mode (selector bit 3 = replicate the sign of the selected byte)
+	static inline unsigned prmt_b32(unsigned a, unsigned b, unsigned s)
+	{
+		uint64_t t = ((uint64_t)b << 32) | a;
+		unsigned r = 0;
+		for (int i = 0; i < 4; ++i) {
+			unsigned sel = (s >> (4 * i)) & 0xF;
+			unsigned byte = (unsigned)(t >> (8 * (sel & 7))) & 0xFF;
+			if (sel & 8)
+				byte = (byte & 0x80) ? 0xFF : 0x00;
+			r |= byte << (8 * i);
+		}
+		return r;
 	}
-	return r;
 }
+// CUDA's __byte_perm only honours the low 3 bits of every selector nibble
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) { return emu::prmt_b32(a, b, s & 0x7777u); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
