@@ -206,27 +206,38 @@ namespace
 
 	bool supported_T(size_t T) { return T == 2 || T == 4 || T == 8; }
 
+#ifndef ENCODE_THREADS_2
+#define ENCODE_THREADS_2 1024
+#endif
+#ifndef ENCODE_THREADS_4
+#define ENCODE_THREADS_4 1024
+#endif
+#ifndef ENCODE_THREADS_8
+#define ENCODE_THREADS_8 512
+#endif
+
 	// ---- launchers ------------------------------------------------------------------------------
-	template<int T>
+	template<int T, int NT>
 	size_t launch_encode_T(stenos_context* ctx, const EncodeParams& P)
 	{
-		const int nthreads = 512;
-		const uint32_t smem = EncodeLayout<T>::smem_bytes(nthreads / 32);
-		if (cudaFuncSetAttribute(encode_frame_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+		const uint32_t smem = EncodeLayout<T>::smem_bytes(NT / 32);
+		if (cudaFuncSetAttribute((const void*)encode_frame_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
 			cudaGetLastError();
 			return STENOS_ERROR_ALLOC;
 		}
+		// persistent CTAs: one per SM (shared-memory slots allow exactly one), superblocks by ticket
 		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, ctx->sm_count));
-		STENOS_LAUNCH(encode_frame_kernel<T>, dim3(grid), dim3(nthreads), smem, ctx->stream(), P);
+		auto kern = encode_frame_kernel<T, NT>;
+		STENOS_LAUNCH(kern, dim3(grid), dim3(NT), smem, ctx->stream(), P);
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 	size_t launch_encode(stenos_context* ctx, size_t T, const EncodeParams& P)
 	{
 		switch (T) {
-			case 2: return launch_encode_T<2>(ctx, P);
-			case 4: return launch_encode_T<4>(ctx, P);
-			case 8: return launch_encode_T<8>(ctx, P);
+			case 2: return launch_encode_T<2, ENCODE_THREADS_2>(ctx, P);
+			case 4: return launch_encode_T<4, ENCODE_THREADS_4>(ctx, P);
+			case 8: return launch_encode_T<8, ENCODE_THREADS_8>(ctx, P);
 		}
 		return STENOS_ERROR_INVALID_PARAMETER;
 	}

@@ -85,6 +85,10 @@ namespace sb
 		return x;
 	}
 
+	// 64-bit flag+value words of the decoupled look-back: single-copy atomic, never cached in L1
+	__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+	__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
 	__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
 	// 4x4 byte transpose: words a,b,c,d (one per element) -> p0..p3 (one per byte plane)

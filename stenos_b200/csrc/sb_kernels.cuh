@@ -127,8 +127,8 @@ namespace sb
 		return nfull * (T * 256u + (T + 1) / 2) + (rem ? 1u + (T + 1) / 2 + 8u * T + rem : 0u);
 	}
 
-	template<int T>
-	__global__ void __launch_bounds__(512, 1) encode_frame_kernel(EncodeParams P)
+	template<int T, int NT>
+	__global__ void __launch_bounds__(NT, 1) encode_frame_kernel(EncodeParams P)
 	{
 		using L = EncodeLayout<T>;
 		STENOS_DYN_SMEM(uint8_t, smem);
@@ -140,15 +140,21 @@ namespace sb
 		uint32_t* lz_scratch = reinterpret_cast<uint32_t*>(smem + L::LZ_OFF + L::LZ_STRIDE * warp);
 		const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
 
+		// tickets are fetched one superblock ahead so the atomic's latency hides behind the encoding
+		uint32_t next_ticket = 0;
+		if (tid == 0)
+			next_ticket = atomicAdd(P.ticket, 1u);
 		for (;;) {
 			// ---- next superblock (ticket order == look-back order: predecessors are always running or done)
 			__syncthreads();
 			if (tid == 0)
-				misc[0] = atomicAdd(P.ticket, 1u);
+				misc[0] = next_ticket;
 			__syncthreads();
 			const uint32_t s = (uint32_t)misc[0];
 			if (s >= P.n_sb)
 				break;
+			if (tid == 0)
+				next_ticket = atomicAdd(P.ticket, 1u);
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
 			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
 			const uint32_t nfull = in_bytes / L::BLOCK, rem = in_bytes - nfull * L::BLOCK;
@@ -167,7 +173,7 @@ namespace sb
 					uint64_t excl = 0;
 					if (s > 0) {
 						unsigned long long v;
-						while (((v = atomicAdd(&P.state[s - 1], 0ull)) & LB_INCLUSIVE) == 0)
+						while (((v = ld_volatile_u64(&P.state[s - 1])) & LB_INCLUSIVE) == 0)
 							STENOS_SPIN_HINT();
 						excl = v & LB_VALUE;
 					}
@@ -247,37 +253,48 @@ namespace sb
 			const bool copy = csize > in_bytes; // stenos.cpp:609-610 (error or larger than the input -> MEMCPY)
 			const uint32_t out_size = 4u + (copy ? in_bytes : csize);
 
-			// ---- frame offset: publish, look back
-			if (tid == 0) {
-				uint64_t excl;
+			// ---- frame offset: publish the size, then a warp-wide decoupled look-back (32 predecessors per probe)
+			if (warp == 0) {
+				uint64_t excl = 0;
 				if (have_base)
 					excl = base - first_off;
 				else {
-					atomicExch(&P.state[s], LB_AGGREGATE | (unsigned long long)out_size);
-					excl = 0;
-					for (long long j = (long long)s - 1; j >= 0;) {
-						const unsigned long long v = atomicAdd(&P.state[j], 0ull);
-						if (v & LB_INCLUSIVE) {
-							excl += v & LB_VALUE;
-							break;
-						}
-						if (v & LB_AGGREGATE) {
-							excl += v & LB_VALUE;
-							--j;
+					if (lane == 0)
+						st_volatile_u64(&P.state[s], LB_AGGREGATE | (unsigned long long)out_size);
+					long long top = (long long)s - 1;
+					while (top >= 0) {
+						const long long idx = top - lane;
+						// entries before the first superblock act as an inclusive prefix of 0
+						const unsigned long long v = idx >= 0 ? ld_volatile_u64(&P.state[idx]) : LB_INCLUSIVE;
+						const uint32_t inc = __ballot_sync(FULL, (v & LB_INCLUSIVE) != 0ull);
+						const uint32_t inv = __ballot_sync(FULL, (v >> 62) == 0ull);
+						const int fi = inc ? (__ffs((int)inc) - 1) : 32; // nearest predecessor that already knows its prefix
+						const uint32_t upto = fi >= 31 ? 0xFFFFFFFFu : ((2u << fi) - 1u);
+						if (inv & upto) { // a predecessor in the window has not published yet
+							STENOS_SPIN_HINT();
 							continue;
 						}
-						STENOS_SPIN_HINT();
+						unsigned long long val = ((upto >> lane) & 1u) ? (v & LB_VALUE) : 0ull;
+#pragma unroll
+						for (int d = 16; d >= 1; d >>= 1)
+							val += __shfl_xor_sync(FULL, val, d);
+						excl += val;
+						if (fi < 32)
+							break;
+						top -= 32;
 					}
 				}
-				atomicExch(&P.state[s], LB_INCLUSIVE | (unsigned long long)(excl + out_size));
-				misc[1] = first_off + excl;
-				if (P.sb_offsets) {
-					P.sb_offsets[s] = first_off + excl;
+				if (lane == 0) {
+					st_volatile_u64(&P.state[s], LB_INCLUSIVE | (unsigned long long)(excl + out_size));
+					misc[1] = first_off + excl;
+					if (P.sb_offsets) {
+						P.sb_offsets[s] = first_off + excl;
+						if (s == P.n_sb - 1)
+							P.sb_offsets[s + 1] = first_off + excl + out_size;
+					}
 					if (s == P.n_sb - 1)
-						P.sb_offsets[s + 1] = first_off + excl + out_size;
+						P.result[0] = first_off + excl + out_size;
 				}
-				if (s == P.n_sb - 1)
-					P.result[0] = first_off + excl + out_size;
 			}
 			__syncthreads();
 			base = misc[1];
