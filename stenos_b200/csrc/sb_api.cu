@@ -120,7 +120,8 @@ struct stenos_context_s
 	size_t superblock = 0;
 	int shift = 0;
 	// scratch
-	DevBuf in, out, ctl, idx;
+	DevBuf in, out, ctl, idx, scan;
+	bool serial_index = false; // tests: force the serial header walk
 	unsigned long long* host_result = nullptr; // pinned, 4 words
 	int sm_count = 0;
 
@@ -190,6 +191,7 @@ struct stenos_context_s
 		out.release();
 		ctl.release();
 		idx.release();
+		scan.release();
 		if (host_result)
 			cudaFreeHost(host_result);
 		host_result = nullptr;
@@ -289,6 +291,52 @@ namespace
 		else
 			cudaMemsetAsync(ctx->ctl.p + 16, 0, bytes - 16, ctx->stream());
 		return true;
+	}
+
+
+	// Superblock index of a device resident frame: parallel re-synchronising scan for large frames,
+	// the serial walk for small ones.  d_offs: [n_sb + 1]; d_result[1] receives error bits.
+	size_t enqueue_index(stenos_context* ctx, const uint8_t* d_src, size_t size, size_t first, size_t n_sb, size_t sb, unsigned long long* d_offs,
+			     unsigned long long* d_result)
+	{
+		cudaStream_t st = ctx->stream();
+		const uint32_t seg = 256u * 1024u;
+		const size_t n_seg = size > first ? (size - first + seg - 1) / seg : 0;
+		if (n_sb < 64 || n_seg < 8 || ctx->serial_index) {
+			IndexParams I;
+			I.src = d_src;
+			I.src_size = size;
+			I.first = first;
+			I.n_sb = (uint32_t)n_sb;
+			I.sb_offsets = d_offs;
+			I.result = d_result;
+			STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
+			++g_launches;
+			return 0;
+		}
+		const uint32_t cap = (uint32_t)std::min<size_t>(n_sb, 2048);
+		const size_t bytes = n_seg * (8 + 8 + 8) + n_seg * (size_t)cap * 8;
+		if (!ctx->scan.reserve(bytes))
+			return STENOS_ERROR_ALLOC;
+		FastIndexParams F;
+		F.src = d_src;
+		F.src_size = size;
+		F.first = first;
+		F.n_sb = (uint32_t)n_sb;
+		F.max_csize = (uint32_t)sb;
+		F.seg_bytes = seg;
+		F.n_seg = (uint32_t)n_seg;
+		F.cap = cap;
+		F.seg_start = reinterpret_cast<unsigned long long*>(ctx->scan.p);
+		F.seg_end = F.seg_start + n_seg;
+		F.seg_count = reinterpret_cast<uint32_t*>(F.seg_end + n_seg);
+		F.seg_list = F.seg_end + 2 * n_seg;
+		F.sb_offsets = d_offs;
+		F.result = d_result;
+		STENOS_LAUNCH(index_scan_kernel, dim3((unsigned)((n_seg + INDEX_WARPS - 1) / INDEX_WARPS)), dim3(INDEX_WARPS * 32), 0, st, F);
+		STENOS_LAUNCH(index_merge_kernel, dim3(1), dim3(1024), 256, st, F);
+		g_launches += 2;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 
 	size_t map_device_error(unsigned long long bits)
@@ -613,15 +661,9 @@ namespace
 			size = used;
 		}
 		else {
-			IndexParams I;
-			I.src = src;
-			I.src_size = size;
-			I.first = first;
-			I.n_sb = (uint32_t)n_sb;
-			I.sb_offsets = d_offs;
-			I.result = d_result;
-			STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
-			++g_launches;
+			const size_t ir = enqueue_index(ctx, src, size, first, n_sb, sb, d_offs, d_result);
+			if (is_err(ir))
+				return ir;
 		}
 
 		// ---- output
@@ -995,16 +1037,8 @@ size_t stenos_b200_frame_index_async(stenos_context* ctx, const void* d_frame, s
 		if (n_sb + 1 > capacity)
 			return STENOS_ERROR_DST_OVERFLOW;
 		cudaMemsetAsync(d_result, 0, 16, st);
-		IndexParams I;
-		I.src = (const uint8_t*)d_frame;
-		I.src_size = frame_bytes;
-		I.first = first;
-		I.n_sb = (uint32_t)n_sb;
-		I.sb_offsets = d_sb_offsets;
-		I.result = d_result;
-		STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
-		++g_launches;
-		return n_sb;
+		const size_t ir = enqueue_index(ctx, (const uint8_t*)d_frame, frame_bytes, first, n_sb, info.superblock_size, d_sb_offsets, d_result);
+		return is_err(ir) ? ir : n_sb;
 	});
 }
 
@@ -1058,16 +1092,11 @@ size_t stenos_b200_decompress_async(stenos_context* ctx, const void* d_src, size
 		if (!offs) {
 			if (!ctx->idx.reserve((n_sb + 1) * 8))
 				return STENOS_ERROR_ALLOC;
-			IndexParams I;
-			I.src = (const uint8_t*)d_src;
-			I.src_size = bytes;
-			I.first = ctx->custom_shift != STENOS_NO_BLOCK_SHIFT ? 12 : 8;
-			I.n_sb = (uint32_t)n_sb;
-			I.sb_offsets = reinterpret_cast<unsigned long long*>(ctx->idx.p);
-			I.result = d_result;
-			STENOS_LAUNCH(frame_index_kernel, dim3(1), dim3(32), 0, st, I);
-			++g_launches;
-			offs = I.sb_offsets;
+			unsigned long long* built = reinterpret_cast<unsigned long long*>(ctx->idx.p);
+			const size_t ir = enqueue_index(ctx, (const uint8_t*)d_src, bytes, ctx->custom_shift != STENOS_NO_BLOCK_SHIFT ? 12 : 8, n_sb, sb, built, d_result);
+			if (is_err(ir))
+				return ir;
+			offs = built;
 		}
 		DecodeParams P;
 		P.src = (const uint8_t*)d_src;

@@ -365,6 +365,190 @@ namespace sb
 	}
 
 	// ------------------------------------------------------------------------------------------
+	// Parallel frame index.  The header chain is a linked list (each [code][csize:3] gives the next
+	// header), which the reference walks serially.  Here the frame is cut in segments; one warp per
+	// segment RE-SYNCHRONISES on the chain by scanning for the first position whose header is
+	// plausible and stays plausible for two more hops, then walks only its own segment.  Plausible is
+	// not proof (payload bytes can imitate headers), so a merge kernel accepts the result only if every
+	// segment's walk lands exactly on the next segment's start, the count equals the superblock count and
+	// the chain ends inside the frame; segment 0 starts at the true first header, so by induction every
+	// accepted header is a true one.  Any inconsistency falls back to the serial walk on the device.
+	// ------------------------------------------------------------------------------------------
+	struct FastIndexParams
+	{
+		const uint8_t* src;
+		uint64_t src_size;
+		uint64_t first;      // offset of the first superblock header
+		uint32_t n_sb;
+		uint32_t max_csize;  // largest plausible payload (the superblock size)
+		uint32_t seg_bytes;
+		uint32_t n_seg;
+		uint32_t cap;        // list capacity per segment
+		unsigned long long* seg_start; // [n_seg]
+		unsigned long long* seg_end;   // [n_seg]
+		uint32_t* seg_count;           // [n_seg]
+		unsigned long long* seg_list;  // [n_seg * cap]
+		unsigned long long* sb_offsets; // [n_sb + 1]
+		unsigned long long* result;
+	};
+	constexpr unsigned long long IDX_NONE = ~0ull;
+	constexpr unsigned long long IDX_BROKEN = ~0ull - 1;
+
+	// next header after the one at `at`, or IDX_BROKEN when `at` cannot be a header
+	__device__ __forceinline__ unsigned long long index_next(const uint8_t* src, uint64_t size, uint64_t at, uint32_t max_csize)
+	{
+		if (at + 4 > size)
+			return IDX_BROKEN;
+		const uint32_t code = src[at];
+		const uint32_t csize = rd24(src + at + 1);
+		if (code < 1u || code > 6u || csize > max_csize || at + 4 + csize > size)
+			return IDX_BROKEN;
+		return at + 4 + csize;
+	}
+
+	constexpr int INDEX_WARPS = 4;
+
+	__global__ void __launch_bounds__(INDEX_WARPS * 32) index_scan_kernel(FastIndexParams P)
+	{
+		const int lane = threadIdx.x & 31;
+		const uint32_t k = blockIdx.x * INDEX_WARPS + (threadIdx.x >> 5);
+		if (k >= P.n_seg)
+			return;
+		const uint64_t lo = P.first + (uint64_t)k * P.seg_bytes;
+		const uint64_t hi = min(lo + (uint64_t)P.seg_bytes, P.src_size); // walk while pos < hi
+		unsigned long long start = IDX_NONE;
+		if (k == 0)
+			start = P.first;
+		else {
+			for (uint64_t x0 = lo; x0 < P.src_size; x0 += 32) {
+				const uint64_t x = x0 + lane;
+				bool ok = false;
+				unsigned long long n1 = index_next(P.src, P.src_size, x, P.max_csize);
+				if (n1 != IDX_BROKEN) {
+					// two more hops (reaching the end of the buffer exactly also counts as plausible)
+					ok = true;
+					unsigned long long at = n1;
+					for (int hop = 0; hop < 2 && ok && at != P.src_size; ++hop) {
+						at = index_next(P.src, P.src_size, at, P.max_csize);
+						ok = at != IDX_BROKEN;
+					}
+				}
+				const uint32_t m = __ballot_sync(FULL, ok);
+				if (m) {
+					start = x0 + (uint32_t)(__ffs((int)m) - 1);
+					break;
+				}
+			}
+		}
+		// walk my own segment
+		unsigned long long pos = start;
+		uint32_t cnt = 0;
+		if (lane == 0) {
+			while (pos != IDX_NONE && pos < hi) {
+				if (cnt < P.cap)
+					P.seg_list[(uint64_t)k * P.cap + cnt] = pos;
+				++cnt;
+				pos = index_next(P.src, P.src_size, pos, P.max_csize);
+				if (pos == IDX_BROKEN)
+					break;
+			}
+			if (cnt > P.cap)
+				pos = IDX_BROKEN;
+			P.seg_start[k] = start;
+			P.seg_end[k] = pos;
+			P.seg_count[k] = cnt;
+		}
+	}
+
+	__global__ void __launch_bounds__(1024) index_merge_kernel(FastIndexParams P)
+	{
+		STENOS_DYN_SMEM(uint32_t, sm); // [0] ok flag, [1] total, [2..2+32) warp sums
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		if (tid == 0)
+			sm[0] = 1u;
+		__syncthreads();
+		// ---- consistency of the hand-offs
+		bool ok = true;
+		for (uint32_t k = tid; k < P.n_seg; k += blockDim.x) {
+			const unsigned long long e = P.seg_end[k];
+			if (e == IDX_BROKEN)
+				ok = false;
+			else if (k + 1 < P.n_seg) {
+				// my walk must land exactly on the next segment's start (IDX_NONE: nothing starts after it)
+				const unsigned long long nx = P.seg_start[k + 1];
+				if (nx == IDX_NONE ? (e != IDX_NONE && e < P.first + (uint64_t)(k + 1) * P.seg_bytes) : (e != nx))
+					ok = false;
+			}
+		}
+		if (!ok)
+			sm[0] = 0u;
+		__syncthreads();
+		// ---- exclusive scan of the counts (n_seg is small: one pass per 1024 segments with a running base)
+		uint32_t base = 0;
+		unsigned long long last_end = P.first;
+		if (sm[0]) {
+			for (uint32_t k0 = 0; k0 < P.n_seg; k0 += blockDim.x) {
+				const uint32_t k = k0 + tid;
+				const uint32_t c = k < P.n_seg ? P.seg_count[k] : 0u;
+				uint32_t incl = c;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t t = __shfl_up_sync(FULL, incl, d);
+					if (lane >= d)
+						incl += t;
+				}
+				if (lane == 31)
+					sm[2 + warp] = incl;
+				__syncthreads();
+				uint32_t wpre = 0, tot = 0;
+				for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+					const uint32_t ws = sm[2 + i];
+					if (i < warp)
+						wpre += ws;
+					tot += ws;
+				}
+				const uint32_t off = base + wpre + incl - c;
+				if (k < P.n_seg && off + c <= P.n_sb)
+					for (uint32_t i = 0; i < c; ++i)
+						P.sb_offsets[off + i] = P.seg_list[(uint64_t)k * P.cap + i];
+				base += tot;
+				__syncthreads();
+			}
+			if (tid == 0) {
+				// the end of the chain: the end of the last segment that has one
+				for (uint32_t k = P.n_seg; k-- > 0;) {
+					if (P.seg_end[k] != IDX_NONE) {
+						last_end = P.seg_end[k];
+						break;
+					}
+				}
+				if (base != P.n_sb || last_end > P.src_size)
+					sm[0] = 0u;
+				else
+					P.sb_offsets[P.n_sb] = last_end;
+			}
+		}
+		__syncthreads();
+		if (!sm[0] && tid == 0) {
+			// fallback: the serial walk (stenos.cpp:1124-1143)
+			uint64_t at = P.first;
+			for (uint32_t i = 0; i < P.n_sb; ++i) {
+				P.sb_offsets[i] = at;
+				if (at + 4 > P.src_size) {
+					atomicOr(&P.result[1], (unsigned long long)DEV_ERR_SRC_OVERFLOW);
+					for (uint32_t j = i; j <= P.n_sb; ++j)
+						P.sb_offsets[j] = P.src_size;
+					return;
+				}
+				at += 4ull + rd24(P.src + at + 1);
+			}
+			P.sb_offsets[P.n_sb] = at;
+			if (at > P.src_size)
+				atomicOr(&P.result[1], (unsigned long long)DEV_ERR_INVALID_INPUT);
+		}
+	}
+
+	// ------------------------------------------------------------------------------------------
 	// decoder: one warp per superblock
 	// ------------------------------------------------------------------------------------------
 	struct DecodeParams

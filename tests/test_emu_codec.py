@@ -144,3 +144,25 @@ def test_filters_match_oracle():
                 assert ctx.unshuffle(np.frombuffer(shd, dtype=np.uint8), T, chunk, True) == a.tobytes()
             assert ctx.delta(a) == port.delta(a)
             assert ctx.delta_inv(np.frombuffer(port.delta(a), dtype=np.uint8)) == a.tobytes()
+
+
+def test_parallel_frame_index_resynchronises_or_falls_back():
+    """Frames whose payload imitates [code][csize:3] headers: the parallel index must still be exact."""
+    ctx = api.Context(block_shift=0)
+    n_sb = 9000
+    res = np.zeros(2, dtype=np.uint64)
+    rng = np.random.default_rng(1)
+    a = rng.integers(-2**31, 2**31, 256 * n_sb).astype(np.int32)
+    a[: 256 * 3000: 3] = 7
+    frames = [port.compress(a, 4, block_shift=0, dst_size=a.nbytes + 8 * n_sb + 64)]
+    for fake in (1, 0x00001001):  # "01 00 00 00" = code 1, csize 0 ; code 1, csize 16 -> plausible multi-hop chains
+        b = np.full(256 * n_sb, fake, dtype=np.int32)
+        frames.append(port.compress(b, 4, level=0, block_shift=0, dst_size=b.nbytes + 8 * n_sb + 64))
+    for frame in frames:
+        f = np.frombuffer(frame, dtype=np.uint8).copy()
+        offs = np.zeros(n_sb + 1, dtype=np.uint64)
+        l0 = api.kernel_launches()
+        assert ctx.frame_index_async(f, len(frame), 4, offs, n_sb + 1, res) == n_sb
+        ctx.synchronize()
+        assert api.kernel_launches() - l0 == 2  # the parallel path (scan + merge), not the serial kernel
+        assert res[1] == 0 and np.array_equal(offs, port.frame_index(frame, 4))

@@ -262,3 +262,28 @@ def test_full_size_roundtrip_properties():
     torch.cuda.synchronize()
     assert d_res.cpu().numpy()[1] == 0
     assert torch.equal(d_out, d_src)
+
+
+def test_parallel_frame_index_on_adversarial_frames():
+    """The device frame index re-synchronises on the header chain in parallel; payloads that imitate
+    headers must not fool it (merge-time verification, serial fallback)."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    ctx = api.Context(stream=torch.cuda.current_stream(), block_shift=0)
+    n_sb = 40000
+    rng = np.random.default_rng(1)
+    a = rng.integers(-2**31, 2**31, 256 * n_sb).astype(np.int32)
+    a[: 256 * 15000: 3] = 7
+    frames = [port.compress(a, 4, block_shift=0, dst_size=a.nbytes + 8 * n_sb + 64)]
+    for fake in (1, 0x00001001, 0x00000406):
+        b = np.full(256 * n_sb, fake, dtype=np.int32)
+        frames.append(port.compress(b, 4, level=0, block_shift=0, dst_size=b.nbytes + 8 * n_sb + 64))
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    for frame in frames:
+        d_f = torch.from_numpy(np.frombuffer(frame, dtype=np.uint8).copy()).to(dev)
+        d_off = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
+        assert ctx.frame_index_async(d_f, len(frame), 4, d_off, n_sb + 1, d_res) == n_sb
+        torch.cuda.synchronize()
+        assert d_res.cpu().numpy()[1] == 0
+        assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), port.frame_index(frame, 4))
