@@ -131,9 +131,14 @@ STENOS_B200_EXPORT size_t stenos_b200_decompress_range_async(stenos_context* ctx
 							    void* d_dst, unsigned long long* d_result);
 /* superblock size the context would use for (bytesoftype, bytes) -- prepare(), stenos.cpp:115-185 */
 STENOS_B200_EXPORT size_t stenos_b200_superblock_size(stenos_context* ctx, size_t bytesoftype, size_t bytes);
-/* Serial walk over the superblock headers of a device-resident frame: d_sb_offsets[count+1]. */
+/* Superblock header offsets of a device-resident frame: d_sb_offsets[count+1] (replaces the serial
+ * walk of stenos.cpp:1124-1143 by a parallel re-synchronising scan that is verified on the device
+ * and falls back to the serial walk when the verification fails). */
 STENOS_B200_EXPORT size_t stenos_b200_frame_index_async(stenos_context* ctx, const void* d_frame, size_t frame_bytes, size_t bytesoftype,
 						       unsigned long long* d_sb_offsets, size_t capacity, unsigned long long* d_result);
+/* Diagnostics: waits for the stream; 1 = the last parallel frame index of this context was accepted,
+ * 0 = it fell back to the serial walk, -1 = no parallel index was run. */
+STENOS_B200_EXPORT int stenos_b200_index_accepted(stenos_context* ctx);
 
 /* Filters (levels >= 2 pre-Zstd stages): stenos::shuffle / unshuffle / delta / delta_inv
  * (stenos/internal/shuffle.h:33,45; delta.h:33,38) applied independently to every `chunk` bytes of

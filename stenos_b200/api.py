@@ -165,6 +165,10 @@ class Context:
         return check(self._lib.stenos_b200_frame_index_async(self._h, ptr_of(d_frame), frame_bytes, bytesoftype, ptr_of(d_sb_offsets), capacity, ptr_of(d_result)),
                      "stenos_b200_frame_index_async")
 
+    def index_accepted(self):
+        """1: the last parallel frame index was accepted, 0: it fell back to the serial walk, -1: none ran."""
+        return int(self._lib.stenos_b200_index_accepted(self._h))
+
     def gather_decode_async(self, d_frame, frame_bytes, bytesoftype, bucket_bytes, out_bytes, d_sb_offsets, n_buckets, d_ids, n, d_dst, d_result):
         return check(self._lib.stenos_b200_gather_decode_async(self._h, ptr_of(d_frame), frame_bytes, bytesoftype, bucket_bytes, out_bytes, ptr_of(d_sb_offsets), n_buckets,
                                                                 ptr_of(d_ids), n, ptr_of(d_dst), ptr_of(d_result)), "stenos_b200_gather_decode_async")

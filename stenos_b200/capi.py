@@ -55,6 +55,7 @@ SIGNATURES = {
     "stenos_b200_decompress_range_async": (_sz, [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _vp]),
     "stenos_b200_superblock_size": (_sz, [_vp, _sz, _sz]),
     "stenos_b200_frame_index_async": (_sz, [_vp, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "stenos_b200_index_accepted": (_ci, [_vp]),
     "stenos_b200_shuffle": (_sz, [_vp, _sz, _sz, _sz, _vp, _vp, _ci]),
     "stenos_b200_unshuffle": (_sz, [_vp, _sz, _sz, _sz, _vp, _vp, _ci]),
     "stenos_b200_delta": (_sz, [_vp, _sz, _sz, _vp, _vp]),

@@ -122,6 +122,7 @@ struct stenos_context_s
 	// scratch
 	DevBuf in, out, ctl, idx, scan;
 	bool serial_index = false; // tests: force the serial header walk
+	bool index_ran = false;    // a parallel frame index was enqueued (its verdict is in scan.p)
 	unsigned long long* host_result = nullptr; // pinned, 4 words
 	int sm_count = 0;
 
@@ -300,8 +301,14 @@ namespace
 			     unsigned long long* d_result)
 	{
 		cudaStream_t st = ctx->stream();
-		const uint32_t seg = 256u * 1024u;
-		const size_t n_seg = size > first ? (size - first + seg - 1) / seg : 0;
+		// segments of about half a superblock: every warp re-synchronises within one superblock and walks a few
+		// hops; at most 65536 segments so the single-CTA merge stays short
+		size_t seg = std::min<size_t>(std::max<size_t>(sb / 2, 4096), 65536);
+		const size_t span = size > first ? size - first : 0;
+		if ((span + seg - 1) / seg > 65536)
+			seg = (span + 65535) / 65536;
+		seg = (seg + 15) & ~(size_t)15;
+		const size_t n_seg = (span + seg - 1) / seg;
 		if (n_sb < 64 || n_seg < 8 || ctx->serial_index) {
 			IndexParams I;
 			I.src = d_src;
@@ -314,8 +321,7 @@ namespace
 			++g_launches;
 			return 0;
 		}
-		const uint32_t cap = (uint32_t)std::min<size_t>(n_sb, 2048);
-		const size_t bytes = n_seg * (8 + 8 + 8) + n_seg * (size_t)cap * 8;
+		const size_t bytes = 16 + n_seg * (8 + 8 + 4 + 4);
 		if (!ctx->scan.reserve(bytes))
 			return STENOS_ERROR_ALLOC;
 		FastIndexParams F;
@@ -323,19 +329,21 @@ namespace
 		F.src_size = size;
 		F.first = first;
 		F.n_sb = (uint32_t)n_sb;
-		F.max_csize = (uint32_t)sb;
-		F.seg_bytes = seg;
+		F.max_csize = (uint32_t)std::min<size_t>(sb, 0xFFFFFFu);
+		F.seg_bytes = (uint32_t)seg;
 		F.n_seg = (uint32_t)n_seg;
-		F.cap = cap;
-		F.seg_start = reinterpret_cast<unsigned long long*>(ctx->scan.p);
+		F.ok = reinterpret_cast<uint32_t*>(ctx->scan.p);
+		F.seg_start = reinterpret_cast<unsigned long long*>(ctx->scan.p + 16);
 		F.seg_end = F.seg_start + n_seg;
 		F.seg_count = reinterpret_cast<uint32_t*>(F.seg_end + n_seg);
-		F.seg_list = F.seg_end + 2 * n_seg;
+		F.seg_base = F.seg_count + n_seg;
 		F.sb_offsets = d_offs;
 		F.result = d_result;
+		ctx->index_ran = true;
 		STENOS_LAUNCH(index_scan_kernel, dim3((unsigned)((n_seg + INDEX_WARPS - 1) / INDEX_WARPS)), dim3(INDEX_WARPS * 32), 0, st, F);
 		STENOS_LAUNCH(index_merge_kernel, dim3(1), dim3(1024), 256, st, F);
-		g_launches += 2;
+		STENOS_LAUNCH(index_fill_kernel, dim3((unsigned)((n_seg + 127) / 128)), dim3(128), 0, st, F);
+		g_launches += 3;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 
@@ -1013,6 +1021,18 @@ size_t stenos_b200_compress_segment_async(stenos_context* ctx, const void* d_src
 			return STENOS_ERROR_INVALID_PARAMETER;
 		return enqueue_encode(ctx, (const uint8_t*)d_src, T, seg_bytes, (uint8_t*)d_dst, dst_size, sb, 0, 0, 0, ctx->level, d_result, d_sb_offsets);
 	});
+}
+
+int stenos_b200_index_accepted(stenos_context* ctx)
+{
+	if (!ctx || !ctx->index_ran || !ctx->scan.p)
+		return -1;
+	if (ctx->device >= 0)
+		cudaSetDevice(ctx->device);
+	uint32_t v = 0;
+	cudaMemcpyAsync(&v, ctx->scan.p, 4, cudaMemcpyDeviceToHost, ctx->stream());
+	cudaStreamSynchronize(ctx->stream());
+	return v ? 1 : 0;
 }
 
 size_t stenos_b200_frame_index_async(stenos_context* ctx, const void* d_frame, size_t frame_bytes, size_t T, unsigned long long* d_sb_offsets, size_t capacity,

@@ -366,13 +366,15 @@ namespace sb
 
 	// ------------------------------------------------------------------------------------------
 	// Parallel frame index.  The header chain is a linked list (each [code][csize:3] gives the next
-	// header), which the reference walks serially.  Here the frame is cut in segments; one warp per
-	// segment RE-SYNCHRONISES on the chain by scanning for the first position whose header is
-	// plausible and stays plausible for two more hops, then walks only its own segment.  Plausible is
-	// not proof (payload bytes can imitate headers), so a merge kernel accepts the result only if every
-	// segment's walk lands exactly on the next segment's start, the count equals the superblock count and
-	// the chain ends inside the frame; segment 0 starts at the true first header, so by induction every
-	// accepted header is a true one.  Any inconsistency falls back to the serial walk on the device.
+	// header), which the reference walks serially (stenos.cpp:1124-1143): 8192 dependent DRAM reads
+	// per GiB.  Here the frame is cut in segments; one warp per segment RE-SYNCHRONISES on the chain
+	// by scanning for the first position that looks like a level-1 header and keeps looking like one
+	// for INDEX_HOPS hops, then walks (counts) only its own segment.  Plausible is not proof (payload
+	// bytes can imitate headers), so a merge kernel accepts the result only if every segment's walk
+	// lands exactly on the next segment's start, the count equals the superblock count and the chain
+	// ends inside the frame; segment 0 starts at the true first header, so by induction every accepted
+	// header is a true one.  A third kernel re-walks the segments and writes the offsets.  Any
+	// inconsistency falls back to the serial walk on the device.
 	// ------------------------------------------------------------------------------------------
 	struct FastIndexParams
 	{
@@ -383,27 +385,58 @@ namespace sb
 		uint32_t max_csize;  // largest plausible payload (the superblock size)
 		uint32_t seg_bytes;
 		uint32_t n_seg;
-		uint32_t cap;        // list capacity per segment
 		unsigned long long* seg_start; // [n_seg]
 		unsigned long long* seg_end;   // [n_seg]
 		uint32_t* seg_count;           // [n_seg]
-		unsigned long long* seg_list;  // [n_seg * cap]
+		uint32_t* seg_base;            // [n_seg] exclusive prefix of the counts
+		uint32_t* ok;                  // [1] set by the merge kernel when the parallel result is accepted
 		unsigned long long* sb_offsets; // [n_sb + 1]
 		unsigned long long* result;
 	};
 	constexpr unsigned long long IDX_NONE = ~0ull;
 	constexpr unsigned long long IDX_BROKEN = ~0ull - 1;
+	constexpr int INDEX_HOPS = 6;
 
-	// next header after the one at `at`, or IDX_BROKEN when `at` cannot be a header
-	__device__ __forceinline__ unsigned long long index_next(const uint8_t* src, uint64_t size, uint64_t at, uint32_t max_csize)
+	// the walk: next header after the one at `at` (bounds only), or IDX_BROKEN
+	__device__ __forceinline__ unsigned long long index_next(const uint8_t* src, uint64_t size, uint64_t at)
 	{
 		if (at + 4 > size)
 			return IDX_BROKEN;
+		const uint64_t end = at + 4 + rd24(src + at + 1);
+		return end > size ? IDX_BROKEN : end;
+	}
+	// the re-synchronisation filter: could `at` be a level-1 superblock header?  (A.2: code 1 with
+	// 1 <= csize <= superblock, code 6 with csize == superblock or ending the frame, code 2 only as
+	// the tiny final superblock.)  Frames holding Zstd codes 3-5 never synchronise and take the serial walk.
+	__device__ __forceinline__ bool index_plausible(const uint8_t* src, uint64_t size, uint64_t at, uint32_t max_csize, unsigned long long& next)
+	{
+		if (at + 4 > size)
+			return false;
 		const uint32_t code = src[at];
 		const uint32_t csize = rd24(src + at + 1);
-		if (code < 1u || code > 6u || csize > max_csize || at + 4 + csize > size)
-			return IDX_BROKEN;
-		return at + 4 + csize;
+		const uint64_t end = at + 4 + csize;
+		next = end;
+		if (end > size)
+			return false;
+		if (code == (uint32_t)CODE_BLOCK)
+			return csize != 0u && csize <= max_csize;
+		if (code == (uint32_t)CODE_COPY)
+			return csize == max_csize || end == size;
+		if (code == (uint32_t)CODE_ZSTD)
+			return end == size && csize <= 256u;
+		return false;
+	}
+	__device__ __forceinline__ bool index_chain_plausible(const uint8_t* src, uint64_t size, uint64_t at, uint32_t max_csize)
+	{
+		unsigned long long nx = 0;
+		for (int hop = 0; hop < INDEX_HOPS; ++hop) {
+			if (!index_plausible(src, size, at, max_csize, nx))
+				return false;
+			if (nx == size)
+				return true; // the chain ends exactly at the end of the frame
+			at = nx;
+		}
+		return true;
 	}
 
 	constexpr int INDEX_WARPS = 4;
@@ -420,40 +453,65 @@ namespace sb
 		if (k == 0)
 			start = P.first;
 		else {
-			for (uint64_t x0 = lo; x0 < P.src_size; x0 += 32) {
-				const uint64_t x = x0 + lane;
-				bool ok = false;
-				unsigned long long n1 = index_next(P.src, P.src_size, x, P.max_csize);
-				if (n1 != IDX_BROKEN) {
-					// two more hops (reaching the end of the buffer exactly also counts as plausible)
-					ok = true;
-					unsigned long long at = n1;
-					for (int hop = 0; hop < 2 && ok && at != P.src_size; ++hop) {
-						at = index_next(P.src, P.src_size, at, P.max_csize);
-						ok = at != IDX_BROKEN;
+			// a true header lies within one superblock (4 + max_csize bytes) of any position inside the chain
+			const uint64_t scan_end = min(P.src_size, (uint64_t)(lo + 4ull + P.max_csize));
+			for (uint64_t x0 = lo; x0 < scan_end; x0 += 32 * 16) {
+				// lane scans 16 consecutive positions; candidates first by their code byte (SWAR), then the chain
+				const uint64_t xb = x0 + 16ull * lane;
+				unsigned long long found = IDX_NONE;
+				uint32_t cand = 0;
+				if (xb < scan_end) {
+					uint32_t w[4];
+					const uint8_t* p = P.src + xb;
+					if (xb + 16 <= P.src_size && (((uintptr_t)p) & 3u) == 0) {
+#pragma unroll
+						for (int j = 0; j < 4; ++j)
+							w[j] = reinterpret_cast<const uint32_t*>(p)[j];
+					}
+					else {
+#pragma unroll
+						for (int j = 0; j < 4; ++j) {
+							uint32_t v = 0;
+#pragma unroll
+							for (int b = 0; b < 4; ++b)
+								v |= (xb + 4 * j + b < P.src_size ? (uint32_t)p[4 * j + b] : 0u) << (8 * b);
+							w[j] = v;
+						}
+					}
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						const uint32_t z = zero_bytes(w[j] ^ 0x01010101u) | zero_bytes(w[j] ^ 0x06060606u) | zero_bytes(w[j] ^ 0x02020202u);
+						cand |= flags_to_mask4(z) << (4 * j);
 					}
 				}
-				const uint32_t m = __ballot_sync(FULL, ok);
+				while (cand) {
+					const uint32_t b = (uint32_t)__ffs((int)cand) - 1u;
+					cand &= cand - 1u;
+					const uint64_t x = xb + b;
+					if (x >= scan_end)
+						break;
+					if (index_chain_plausible(P.src, P.src_size, x, P.max_csize)) {
+						found = x;
+						break;
+					}
+				}
+				const uint32_t m = __ballot_sync(FULL, found != IDX_NONE);
 				if (m) {
-					start = x0 + (uint32_t)(__ffs((int)m) - 1);
+					start = __shfl_sync(FULL, found, __ffs((int)m) - 1);
 					break;
 				}
 			}
 		}
-		// walk my own segment
-		unsigned long long pos = start;
-		uint32_t cnt = 0;
+		// count the headers of my own segment
 		if (lane == 0) {
+			unsigned long long pos = start;
+			uint32_t cnt = 0;
 			while (pos != IDX_NONE && pos < hi) {
-				if (cnt < P.cap)
-					P.seg_list[(uint64_t)k * P.cap + cnt] = pos;
 				++cnt;
-				pos = index_next(P.src, P.src_size, pos, P.max_csize);
+				pos = index_next(P.src, P.src_size, pos);
 				if (pos == IDX_BROKEN)
 					break;
 			}
-			if (cnt > P.cap)
-				pos = IDX_BROKEN;
 			P.seg_start[k] = start;
 			P.seg_end[k] = pos;
 			P.seg_count[k] = cnt;
@@ -462,30 +520,60 @@ namespace sb
 
 	__global__ void __launch_bounds__(1024) index_merge_kernel(FastIndexParams P)
 	{
-		STENOS_DYN_SMEM(uint32_t, sm); // [0] ok flag, [1] total, [2..2+32) warp sums
+		STENOS_DYN_SMEM(uint32_t, sm); // [0] ok flag, [2..2+32) warp sums
 		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 		if (tid == 0)
 			sm[0] = 1u;
 		__syncthreads();
-		// ---- consistency of the hand-offs
-		bool ok = true;
-		for (uint32_t k = tid; k < P.n_seg; k += blockDim.x) {
-			const unsigned long long e = P.seg_end[k];
-			if (e == IDX_BROKEN)
-				ok = false;
-			else if (k + 1 < P.n_seg) {
-				// my walk must land exactly on the next segment's start (IDX_NONE: nothing starts after it)
+		// ---- consistency of the hand-offs.  My walk must land exactly on the next segment's start; once the
+		// chain has reached the end of the frame the remaining segments must have found nothing.  A segment
+		// that re-synchronised on an imitation (structured payloads do contain plausible 6-hop chains) is
+		// REPAIRED: it is walked again from where its predecessor landed.  Segment 0 is always right, so each
+		// round fixes at least the first wrong segment; the rounds are bounded, then the serial walk takes over.
+		for (int round = 0; round < 64; ++round) {
+			if (tid == 0)
+				sm[1] = 0u;
+			__syncthreads();
+			for (uint32_t k = tid; k + 1 < P.n_seg; k += blockDim.x) {
+				const unsigned long long e = P.seg_end[k];
 				const unsigned long long nx = P.seg_start[k + 1];
-				if (nx == IDX_NONE ? (e != IDX_NONE && e < P.first + (uint64_t)(k + 1) * P.seg_bytes) : (e != nx))
-					ok = false;
+				const unsigned long long want = (e == P.src_size || e == IDX_NONE) ? IDX_NONE : e;
+				const bool bad = e != IDX_BROKEN && nx != want;
+				P.seg_base[k + 1] = bad ? 1u : 0u;
+				if (bad)
+					sm[1] = 1u;
 			}
+			__syncthreads();
+			if (!sm[1])
+				break;
+			for (uint32_t k = tid; k + 1 < P.n_seg; k += blockDim.x) {
+				if (!P.seg_base[k + 1])
+					continue;
+				const unsigned long long e = P.seg_end[k];
+				const uint64_t hi = min(P.first + (uint64_t)(k + 2) * P.seg_bytes, P.src_size);
+				unsigned long long pos = (e == P.src_size || e == IDX_NONE) ? IDX_NONE : e;
+				P.seg_start[k + 1] = pos;
+				uint32_t cnt = 0;
+				while (pos != IDX_NONE && pos < hi) {
+					++cnt;
+					pos = index_next(P.src, P.src_size, pos);
+					if (pos == IDX_BROKEN)
+						break;
+				}
+				P.seg_end[k + 1] = pos;
+				P.seg_count[k + 1] = cnt;
+			}
+			__syncthreads();
 		}
+		bool ok = sm[1] == 0u;
+		for (uint32_t k = tid; k < P.n_seg; k += blockDim.x)
+			if (P.seg_end[k] == IDX_BROKEN)
+				ok = false;
 		if (!ok)
 			sm[0] = 0u;
 		__syncthreads();
-		// ---- exclusive scan of the counts (n_seg is small: one pass per 1024 segments with a running base)
+		// ---- exclusive scan of the counts, 1024 segments per pass with a running base
 		uint32_t base = 0;
-		unsigned long long last_end = P.first;
 		if (sm[0]) {
 			for (uint32_t k0 = 0; k0 < P.n_seg; k0 += blockDim.x) {
 				const uint32_t k = k0 + tid;
@@ -507,21 +595,15 @@ namespace sb
 						wpre += ws;
 					tot += ws;
 				}
-				const uint32_t off = base + wpre + incl - c;
-				if (k < P.n_seg && off + c <= P.n_sb)
-					for (uint32_t i = 0; i < c; ++i)
-						P.sb_offsets[off + i] = P.seg_list[(uint64_t)k * P.cap + i];
+				if (k < P.n_seg)
+					P.seg_base[k] = min(base + wpre + incl - c, P.n_sb); // clamped: a wrong total is rejected below
 				base += tot;
 				__syncthreads();
 			}
 			if (tid == 0) {
-				// the end of the chain: the end of the last segment that has one
-				for (uint32_t k = P.n_seg; k-- > 0;) {
-					if (P.seg_end[k] != IDX_NONE) {
-						last_end = P.seg_end[k];
-						break;
-					}
-				}
+				unsigned long long last_end = P.seg_end[P.n_seg - 1];
+				if (last_end == IDX_NONE)
+					last_end = P.src_size;
 				if (base != P.n_sb || last_end > P.src_size)
 					sm[0] = 0u;
 				else
@@ -529,6 +611,8 @@ namespace sb
 			}
 		}
 		__syncthreads();
+		if (tid == 0)
+			*P.ok = sm[0];
 		if (!sm[0] && tid == 0) {
 			// fallback: the serial walk (stenos.cpp:1124-1143)
 			uint64_t at = P.first;
@@ -545,6 +629,21 @@ namespace sb
 			P.sb_offsets[P.n_sb] = at;
 			if (at > P.src_size)
 				atomicOr(&P.result[1], (unsigned long long)DEV_ERR_INVALID_INPUT);
+		}
+	}
+
+	// accepted: every segment walks its headers again (L2 hits) and writes them at its base
+	__global__ void __launch_bounds__(128) index_fill_kernel(FastIndexParams P)
+	{
+		const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+		if (k >= P.n_seg || *P.ok == 0u)
+			return;
+		const uint32_t cnt = P.seg_count[k];
+		uint32_t at_i = P.seg_base[k];
+		unsigned long long pos = P.seg_start[k];
+		for (uint32_t i = 0; i < cnt && at_i < P.n_sb; ++i, ++at_i) {
+			P.sb_offsets[at_i] = pos;
+			pos = index_next(P.src, P.src_size, pos);
 		}
 	}
 

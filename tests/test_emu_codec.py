@@ -158,11 +158,13 @@ def test_parallel_frame_index_resynchronises_or_falls_back():
     for fake in (1, 0x00001001):  # "01 00 00 00" = code 1, csize 0 ; code 1, csize 16 -> plausible multi-hop chains
         b = np.full(256 * n_sb, fake, dtype=np.int32)
         frames.append(port.compress(b, 4, level=0, block_shift=0, dst_size=b.nbytes + 8 * n_sb + 64))
-    for frame in frames:
+    for i, frame in enumerate(frames):
         f = np.frombuffer(frame, dtype=np.uint8).copy()
         offs = np.zeros(n_sb + 1, dtype=np.uint64)
         l0 = api.kernel_launches()
         assert ctx.frame_index_async(f, len(frame), 4, offs, n_sb + 1, res) == n_sb
         ctx.synchronize()
-        assert api.kernel_launches() - l0 == 2  # the parallel path (scan + merge), not the serial kernel
+        assert api.kernel_launches() - l0 == 3  # the parallel path (scan + merge + fill), not the serial kernel
         assert res[1] == 0 and np.array_equal(offs, port.frame_index(frame, 4))
+        if i == 0:
+            assert ctx.index_accepted() == 1  # an ordinary frame must not need the serial fallback

@@ -280,10 +280,12 @@ def test_parallel_frame_index_on_adversarial_frames():
         b = np.full(256 * n_sb, fake, dtype=np.int32)
         frames.append(port.compress(b, 4, level=0, block_shift=0, dst_size=b.nbytes + 8 * n_sb + 64))
     d_res = torch.zeros(2, dtype=torch.int64, device=dev)
-    for frame in frames:
+    for i, frame in enumerate(frames):
         d_f = torch.from_numpy(np.frombuffer(frame, dtype=np.uint8).copy()).to(dev)
         d_off = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
         assert ctx.frame_index_async(d_f, len(frame), 4, d_off, n_sb + 1, d_res) == n_sb
         torch.cuda.synchronize()
         assert d_res.cpu().numpy()[1] == 0
         assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), port.frame_index(frame, 4))
+        if i == 0:
+            assert ctx.index_accepted() == 1  # an ordinary frame is indexed by the parallel path, no serial fallback
