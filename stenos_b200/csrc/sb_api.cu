@@ -213,10 +213,10 @@ namespace
 #define ENCODE_THREADS_2 1024
 #endif
 #ifndef ENCODE_THREADS_4
-#define ENCODE_THREADS_4 1024
+#define ENCODE_THREADS_4 512
 #endif
 #ifndef ENCODE_THREADS_8
-#define ENCODE_THREADS_8 512
+#define ENCODE_THREADS_8 256
 #endif
 
 	// ---- launchers ------------------------------------------------------------------------------

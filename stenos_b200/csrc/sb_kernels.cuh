@@ -13,6 +13,7 @@
 #pragma once
 #include "sb_common.cuh"
 #include "sb_encode.cuh"
+#include "sb_encode_rows.cuh"
 #include "sb_decode.cuh"
 
 namespace sb
@@ -190,13 +191,16 @@ namespace sb
 			if (P.level == 0) {
 			}
 			else if (!exact) {
-				for (uint32_t b = warp; b < nfull; b += nwarps) {
-					bool e = false;
-					const uint32_t sz = encode_block<T, false>(in + (size_t)b * L::BLOCK, smem + b * L::STRIDE, lz_scratch, lane, 0xFFFFFFFFu, e);
-					if (lane == 0)
-						sizes[b] = sz;
+				// full blocks in pairs: one warp per pair, one lane per 16-element row (sb_encode_rows.cuh)
+				const uint32_t npairs = (nfull + 1u) >> 1;
+				for (uint32_t pr = warp; pr < npairs; pr += nwarps) {
+					const uint32_t b = 2u * pr;
+					const bool second = b + 1u < nfull;
+					const uint32_t sz = encode_block_pair<T>(in + (size_t)b * L::BLOCK, second, smem + b * L::STRIDE, L::STRIDE, lz_scratch, lane);
+					if ((lane & 15) == 0 && (lane == 0 || second))
+						sizes[b + (lane >> 4)] = sz;
 				}
-				if (rem && warp == (int)(nfull % nwarps)) {
+				if (rem && warp == (int)(npairs % nwarps)) {
 					bool e = false;
 					const uint32_t sz = encode_partial_block<T, false>(in + (size_t)nfull * L::BLOCK, rem, smem + nfull * L::STRIDE, lane, 0xFFFFFFFFu, e);
 					if (lane == 0)
