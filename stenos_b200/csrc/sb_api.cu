@@ -7,6 +7,7 @@
 // superblock shorter than 128 bytes (stenos.cpp:435-437), which the reference delegates to libzstd
 // as well -- here through dlopen("libzstd.so.1").
 #include "sb_kernels.cuh"
+#include "sb_stream.cuh"
 #include "sb_filters.cuh"
 #include "../../include/stenos_b200.h"
 
@@ -122,6 +123,8 @@ struct stenos_context_s
 	// scratch
 	DevBuf in, out, ctl, idx, scan;
 	bool serial_index = false; // tests: force the serial header walk
+	bool legacy_encoder = false; // tests: every superblock through encode_frame_kernel
+	bool env_read = false;
 	bool index_ran = false;    // a parallel frame index was enqueued (its verdict is in scan.p)
 	unsigned long long* host_result = nullptr; // pinned, 4 words
 	int sm_count = 0;
@@ -139,6 +142,12 @@ struct stenos_context_s
 	}
 	bool activate()
 	{
+		if (!env_read) {
+			// test hook: STENOS_B200_LEGACY_ENCODER=1 sends every superblock through encode_frame_kernel
+			const char* e = getenv("STENOS_B200_LEGACY_ENCODER");
+			legacy_encoder = e && e[0] == '1';
+			env_read = true;
+		}
 		if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
 			cudaGetLastError();
 			return false;
@@ -218,6 +227,15 @@ namespace
 #ifndef ENCODE_THREADS_8
 #define ENCODE_THREADS_8 256
 #endif
+#ifndef STREAM_THREADS_2
+#define STREAM_THREADS_2 1024
+#endif
+#ifndef STREAM_THREADS_4
+#define STREAM_THREADS_4 512
+#endif
+#ifndef STREAM_THREADS_8
+#define STREAM_THREADS_8 256
+#endif
 
 	// ---- launchers ------------------------------------------------------------------------------
 	template<int T, int NT>
@@ -229,14 +247,55 @@ namespace
 			return STENOS_ERROR_ALLOC;
 		}
 		// persistent CTAs: one per SM (shared-memory slots allow exactly one), superblocks by ticket
-		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, ctx->sm_count));
+		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb - P.first_sb, ctx->sm_count));
 		auto kern = encode_frame_kernel<T, NT>;
 		STENOS_LAUNCH(kern, dim3(grid), dim3(NT), smem, ctx->stream(), P);
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
-	size_t launch_encode(stenos_context* ctx, size_t T, const EncodeParams& P)
+	template<int T, int NT>
+	size_t launch_stream_T(stenos_context* ctx, const EncodeParams& P)
 	{
+		const uint32_t smem = StreamLayout<T, NT>::smem_bytes();
+		if (cudaFuncSetAttribute((const void*)encode_stream_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_ALLOC;
+		}
+		// persistent CTAs, one per SM (the shared-memory ring takes the SM); CTA c owns superblocks c, c + grid, ...
+		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_stream, ctx->sm_count));
+		auto kern = encode_stream_kernel<T, NT>;
+		STENOS_LAUNCH(kern, dim3(grid), dim3(NT), smem, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+	// Superblocks [0, n_stream) go through the barrier-free pipeline (encode_stream_kernel); the ones whose
+	// dst room could change an encoder decision -- and level 0 -- through
+	// encode_frame_kernel, which continues the same look-back chain.
+	size_t launch_encode(stenos_context* ctx, size_t T, EncodeParams P)
+	{
+		uint32_t n_stream = 0;
+		if (P.level != 0 && !ctx->legacy_encoder) {
+			const uint64_t block = T * 256, hs = (T + 1) / 2;
+			const uint64_t need = (P.sb_bytes / block) * (block + hs) + 8 * T + 32 + 8 * T + block; // worst stream + slack (+ a partial block's worst case)
+			const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
+			if (P.dst_size >= first_off + 4 + need) {
+				const uint64_t k = (P.dst_size - first_off - 4 - need) / (4ull + P.sb_bytes) + 1; // superblocks 0..k-1 have room even after k-1 COPY superblocks
+				n_stream = (uint32_t)std::min<uint64_t>(k, P.n_sb);
+			}
+		}
+		P.n_stream = n_stream;
+		P.first_sb = n_stream;
+		size_t r = 0;
+		if (n_stream) {
+			switch (T) {
+				case 2: r = launch_stream_T<2, STREAM_THREADS_2>(ctx, P); break;
+				case 4: r = launch_stream_T<4, STREAM_THREADS_4>(ctx, P); break;
+				case 8: r = launch_stream_T<8, STREAM_THREADS_8>(ctx, P); break;
+				default: return STENOS_ERROR_INVALID_PARAMETER;
+			}
+			if (is_err(r) || n_stream == P.n_sb)
+				return r;
+		}
 		switch (T) {
 			case 2: return launch_encode_T<2, ENCODE_THREADS_2>(ctx, P);
 			case 4: return launch_encode_T<4, ENCODE_THREADS_4>(ctx, P);

@@ -182,21 +182,24 @@ namespace sb
 	}
 
 	// ------------------------------------------------------------------------------------------
-	// Two full 256-element blocks -> their slots (shared memory).  blk0 / slot0: block and slot of the
-	// lower half-warp; the upper half-warp works on blk0 + T*256 / slot0 + slot_stride when
-	// `second` is set, else it shadows the lower half without writing.  Ample dst room is assumed
-	// (the caller proved the reference's room checks inert).
+	// Two full 256-element blocks -> shared memory.  blk0: block of the lower half-warp; the upper
+	// half-warp works on blk0 + T*256 when `second` is set, else it shadows the lower half without
+	// writing.  Everything is sized first; then place(size) -- called once, convergently, with the
+	// lane's block size (uniform over each half-warp) -- returns where the lane's block goes (or
+	// nullptr when its bytes are not wanted).  LZ streams, whose size is only known once they exist,
+	// are built at tmp0 + half * tmp_stride and moved.  Ample dst room is assumed (the caller proved
+	// the reference's room checks inert).
 	// Returns the encoded size of the lane's block (uniform over each half-warp).
 	// ------------------------------------------------------------------------------------------
-	template<int T>
-	__device__ __forceinline__ uint32_t encode_block_pair(const uint8_t* __restrict__ blk0, bool second, uint8_t* slot0, uint32_t slot_stride, uint32_t* lz_scratch, int lane)
+	template<int T, class Place>
+	__device__ __forceinline__ uint32_t encode_block_pair(const uint8_t* __restrict__ blk0, bool second, uint8_t* tmp0, uint32_t tmp_stride, uint32_t* lz_scratch, int lane,
+							      Place&& place)
 	{
 		constexpr uint32_t HS = (T + 1) / 2;
 		const int hb = lane >> 4, r = lane & 15;
 		const bool upper = hb && second;
 		const bool writer = !hb || second;
 		const uint8_t* blk = upper ? blk0 + T * 256 : blk0;
-		uint8_t* slot = upper ? slot0 + slot_stride : slot0;
 		const uint32_t below = (1u << r) - 1u; // rows before mine
 
 		uint32_t pw[T][4];
@@ -300,7 +303,7 @@ namespace sb
 					if (!((want >> (16 * hh)) & 1u) || (hh && !second))
 						continue;
 					const uint8_t* gs = blk0 + (size_t)hh * T * 256;
-					uint8_t* sl = slot0 + (size_t)hh * slot_stride;
+					uint8_t* sl = tmp0 + (size_t)hh * tmp_stride;
 					const uint32_t fmax = __shfl_sync(FULL, full, 16 * hh);
 					uint32_t w[2 * T];
 					load_lane_words<T>(gs, lane, w);
@@ -319,8 +322,29 @@ namespace sb
 			}
 		}
 
+		// ---- placement: the sizes of both blocks are final; the caller says where the lane's block goes
+		// (nullptr: the bytes are not wanted).  LZ streams were built in the temporary and move now.
+		uint8_t* slot = place(size);
+		if ((T % 4) == 0) {
+			const uint32_t lzm = __ballot_sync(FULL, lz_done);
+			if (lzm) {
+#pragma unroll 1
+				for (int hh = 0; hh < 2; ++hh) {
+					if (!((lzm >> (16 * hh)) & 1u))
+						continue;
+					uint8_t* to = reinterpret_cast<uint8_t*>(__shfl_sync(FULL, (unsigned long long)(uintptr_t)slot, 16 * hh));
+					const uint8_t* from = tmp0 + (size_t)hh * tmp_stride;
+					const uint32_t n = __shfl_sync(FULL, size, 16 * hh);
+					if (to && to != from)
+						for (uint32_t i = lane; i < n; i += 32)
+							to[i] = from[i];
+				}
+				__syncwarp();
+			}
+		}
+
 		// ---- emission (encode16x16_generic, :739-806)
-		const bool emit = writer && !lz_done;
+		const bool emit = writer && !lz_done && slot != nullptr;
 		if (emit && r == 0) {
 #pragma unroll
 			for (uint32_t i = 0; i < HS; ++i)

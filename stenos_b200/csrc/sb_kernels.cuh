@@ -97,6 +97,8 @@ namespace sb
 		unsigned long long* result; // [0] offset past the last superblock written, [1] device error bits
 		unsigned long long* sb_offsets; // optional [n_sb + 1]: offset of every superblock header in dst
 		uint64_t base_offset; // offset in dst of this launch's first superblock when header_len == 0 (multi-GPU segments)
+		uint32_t first_sb;    // encode_frame_kernel: superblocks [first_sb, n_sb) (the ones before were placed by encode_stream_kernel)
+		uint32_t n_stream;    // encode_stream_kernel: superblocks [0, n_stream)
 	};
 
 	constexpr unsigned long long LB_AGGREGATE = 1ull << 62;
@@ -108,7 +110,8 @@ namespace sb
 	{
 		static constexpr uint32_t BLOCK = T * 256u;
 		static constexpr uint32_t HS = (T + 1) / 2;
-		static constexpr uint32_t STRIDE = (BLOCK + HS + 1u + 15u) & ~15u; // worst block / partial encoding, 16-byte aligned
+		// worst full block BLOCK + HS (LZ: 1 + BLOCK); worst partial block 1 + HS + 8 * T + (BLOCK - 1); 16-byte aligned
+		static constexpr uint32_t STRIDE = (BLOCK + HS + 8u * T + 1u + 15u) & ~15u;
 		static constexpr uint32_t MAX_BLOCKS = DEFAULT_SUPERBLOCK / BLOCK;
 		static constexpr uint32_t SLOTS_BYTES = MAX_BLOCKS * STRIDE;
 		static constexpr uint32_t NENT = MAX_BLOCKS + 1; // + partial
@@ -144,7 +147,7 @@ namespace sb
 		// tickets are fetched one superblock ahead so the atomic's latency hides behind the encoding
 		uint32_t next_ticket = 0;
 		if (tid == 0)
-			next_ticket = atomicAdd(P.ticket, 1u);
+			next_ticket = P.first_sb + atomicAdd(P.ticket, 1u);
 		for (;;) {
 			// ---- next superblock (ticket order == look-back order: predecessors are always running or done)
 			__syncthreads();
@@ -155,7 +158,7 @@ namespace sb
 			if (s >= P.n_sb)
 				break;
 			if (tid == 0)
-				next_ticket = atomicAdd(P.ticket, 1u);
+				next_ticket = P.first_sb + atomicAdd(P.ticket, 1u);
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
 			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
 			const uint32_t nfull = in_bytes / L::BLOCK, rem = in_bytes - nfull * L::BLOCK;
@@ -196,7 +199,9 @@ namespace sb
 				for (uint32_t pr = warp; pr < npairs; pr += nwarps) {
 					const uint32_t b = 2u * pr;
 					const bool second = b + 1u < nfull;
-					const uint32_t sz = encode_block_pair<T>(in + (size_t)b * L::BLOCK, second, smem + b * L::STRIDE, L::STRIDE, lz_scratch, lane);
+					uint8_t* slot0 = smem + b * L::STRIDE;
+					const uint32_t sz = encode_block_pair<T>(in + (size_t)b * L::BLOCK, second, slot0, L::STRIDE, lz_scratch, lane,
+										 [&](uint32_t) -> uint8_t* { return ((lane >> 4) && second) ? slot0 + L::STRIDE : slot0; });
 					if ((lane & 15) == 0 && (lane == 0 || second))
 						sizes[b + (lane >> 4)] = sz;
 				}

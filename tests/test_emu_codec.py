@@ -168,3 +168,28 @@ def test_parallel_frame_index_resynchronises_or_falls_back():
         assert res[1] == 0 and np.array_equal(offs, port.frame_index(frame, 4))
         if i == 0:
             assert ctx.index_accepted() == 1  # an ordinary frame must not need the serial fallback
+
+
+def _mixed(T, n_sb, seed, tail_elems):
+    """n_sb superblocks that alternate between incompressible, LZ-friendly and well compressible data + a partial tail."""
+    per = 131072 // T
+    kinds = ["random", "ramp_noise16", "random", "lz_then_noise", "random", "random", "sparse_changes", "mostly_random_some_repeats", "const"]
+    parts = [raw_of(dists.make(kinds[(i + seed) % len(kinds)], per, T, seed=seed + i)) for i in range(n_sb)]
+    if tail_elems:
+        parts.append(raw_of(dists.make("random" if seed & 1 else "ramp_noise16", tail_elems, T, seed=seed)))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("T,n_sb,tail", [(4, 11, 255 * 4 // 4), (8, 7, 37), (2, 6, 0)])
+def test_stream_encoder_ring_wrap_copy_superblocks_and_tail(T, n_sb, tail):
+    """encode_stream_kernel: ample dst room -> every superblock goes through the barrier-free pipeline; runs of
+    incompressible superblocks fill the shared-memory ring (wrap, waits for flushes), COPY decisions, partial tail."""
+    raw = _mixed(T, n_sb, seed=T, tail_elems=tail)
+    room = raw.size + 300000
+    want = port.compress(raw, T, dst_size=room)
+    ctx = api.Context()
+    l0 = api.kernel_launches()
+    got = ctx.compress(raw, T, dst_size=room)
+    assert api.kernel_launches() - l0 == 1  # the stream kernel alone
+    assert got == want
+    assert api.decompress(got, T, raw.size) == raw.tobytes()
