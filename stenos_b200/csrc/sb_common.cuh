@@ -10,6 +10,7 @@
 #ifdef STENOS_EMU
 #include "cuda_emu.h"
 #define STENOS_SPIN_HINT() emu::yield()
+#define STENOS_SPIN_WAIT() emu::yield()
 #else
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -19,6 +20,7 @@
 	type* name = reinterpret_cast<type*>(stenos_dyn_smem_raw)
 #define STENOS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define STENOS_SPIN_HINT() __nanosleep(20)
+#define STENOS_SPIN_WAIT() __nanosleep(200) // waits that are expected to be long
 #endif
 
 namespace sb

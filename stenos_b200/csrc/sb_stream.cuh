@@ -5,8 +5,9 @@
 // whose dst-room checks are provably inert; the few that are not are left to
 // encode_frame_kernel, which shares the look-back words.
 //
-// Persistent CTAs, superblock s = blockIdx.x + q * gridDim.x for q = 0, 1, ...  Inside a CTA nothing
-// ever waits for the whole CTA:
+// Persistent CTAs; a CTA's q-th superblock is blockIdx.x for q = 0 and then whatever the global
+// ticket counter hands out (fetched one superblock ahead), so CTAs that meet cheap superblocks simply
+// take more of them.  Inside a CTA nothing ever waits for the whole CTA:
 //
 //   * warps take TICKETS from a shared-memory counter; ticket t = (q, j) is pair j of two
 //     256-element blocks of the CTA's q-th superblock (the slot after the last pair is the partial
@@ -37,13 +38,15 @@ namespace sb
 		unsigned long long start; // START_READY | ring position (absolute, monotonic) of the superblock's stream
 		uint32_t done;            // tickets completed
 		uint32_t cross_end;       // absolute end of the block that ran into the ring's linear tail (0: none)
+		uint32_t sb_plus1;        // 1 + the superblock this slot works on (0: not assigned yet)
+		uint32_t pad[3];
 	};
 	struct StreamCtl
 	{
 		uint32_t ticket;
 		uint32_t flushed_q;   // superblocks [0, flushed_q) of this CTA are flushed, their slots reusable
 		uint32_t flushed_abs; // ring bytes below this absolute position are free
-		uint32_t pad;
+		uint32_t finished;    // a ticket met a superblock past the end
 	};
 
 	template<int T, int NT>
@@ -53,13 +56,13 @@ namespace sb
 		static constexpr uint32_t HS = (T + 1) / 2;
 		static constexpr uint32_t NWARPS = NT / 32;
 		static constexpr uint32_t TMP = (BLOCK + HS + 8u * T + 1u + 15u) & ~15u; // worst block / partial block, 16-byte aligned
-		static constexpr uint32_t NSLOT = 4;
+		static constexpr uint32_t NSLOT = 8;
 		static constexpr uint32_t PMAX = DEFAULT_SUPERBLOCK / BLOCK / 2 + 1; // tickets per superblock: pairs + the partial block
 		static constexpr uint32_t HAS_LZ = (T % 4) == 0 ? 1u : 0u;
 		static constexpr uint32_t LZ_STRIDE = (LZ_SCRATCH_BYTES + 15u) & ~15u;
 		static constexpr uint32_t CTL_OFF = 0;
 		static constexpr uint32_t SLOT_OFF = 16;
-		static constexpr uint32_t CHAIN_OFF = SLOT_OFF + NSLOT * 16u;
+		static constexpr uint32_t CHAIN_OFF = SLOT_OFF + NSLOT * 32u;
 		static constexpr uint32_t TMP_OFF = (CHAIN_OFF + NSLOT * PMAX * 4u + 15u) & ~15u;
 		static constexpr uint32_t LZ_OFF = TMP_OFF + NWARPS * 2u * TMP;
 		static constexpr uint32_t RING_OFF = LZ_OFF + HAS_LZ * NWARPS * LZ_STRIDE;
@@ -146,29 +149,56 @@ namespace sb
 		for (uint32_t i = tid; i < (L::TMP_OFF - L::CTL_OFF) / 4u; i += blockDim.x)
 			reinterpret_cast<uint32_t*>(smem)[i] = 0u;
 		__syncthreads();
-		if (tid == 0)
+		if (tid == 0) {
 			slots[0].start = START_READY;
+			slots[0].sb_plus1 = blockIdx.x + 1u;
+		}
 		__syncthreads();
 
 		// tickets per superblock: the pairs of a full superblock + one for a partial tail block
 		const uint32_t nfull_sb = P.sb_bytes / L::BLOCK;
 		const uint32_t PT = (nfull_sb + 1u) / 2u + 1u;
+		const uint32_t PT_RCP = (uint32_t)((0x100000000ull + PT - 1u) / PT); // t / PT == umulhi(t, PT_RCP) for t < 2^32 / PT
 
 		for (;;) {
 			uint32_t t = 0;
 			if (lane == 0)
 				t = atomicAdd(&ctl->ticket, 1u);
 			t = __shfl_sync(FULL, t, 0);
-			const uint32_t q = t / PT, j = t - q * PT;
-			const uint64_t s64 = (uint64_t)blockIdx.x + (uint64_t)q * gridDim.x;
-			if (s64 >= (uint64_t)P.n_stream)
+			const uint32_t q = __umulhi(t, PT_RCP), j = t - q * PT;
+			// the slot of q and the one of q + 1 (whose superblock and start are published from q) must be free
+			bool finished = false;
+			while ((int)(q - *v_flushed_q) >= (int)L::NSLOT - 1) {
+				if (*reinterpret_cast<volatile uint32_t*>(&ctl->finished)) { // nothing is left for this CTA: the slot will never come
+					finished = true;
+					break;
+				}
+				STENOS_SPIN_WAIT();
+			}
+			if (finished)
 				break;
-			const uint32_t s = (uint32_t)s64;
-			// the slot of q and the one of q + 1 (whose start this superblock publishes) must be free
-			while ((int)(q - *v_flushed_q) >= (int)L::NSLOT - 1)
-				STENOS_SPIN_HINT();
 			StreamSlot* slot = &slots[q % L::NSLOT];
 			uint32_t* chain = chains + (q % L::NSLOT) * L::PMAX;
+			if (j == 0 && lane == 0) {
+				// the next superblock of this CTA, one superblock ahead of its first use
+				const uint32_t nx = gridDim.x + atomicAdd(P.ticket + 1, 1u); // [1]: [0] belongs to encode_frame_kernel
+				*reinterpret_cast<volatile uint32_t*>(&slots[(q + 1u) % L::NSLOT].sb_plus1) = nx + 1u;
+			}
+			uint32_t s;
+			while ((s = *reinterpret_cast<volatile uint32_t*>(&slot->sb_plus1)) == 0u) {
+				if (*reinterpret_cast<volatile uint32_t*>(&ctl->finished)) {
+					s = 0xFFFFFFFFu;
+					break;
+				}
+				STENOS_SPIN_HINT();
+			}
+			s -= 1u;
+			if (s >= P.n_stream) {
+				// superblocks are handed out in increasing order: every later ticket of this CTA is past the end too
+				if (lane == 0)
+					*reinterpret_cast<volatile uint32_t*>(&ctl->finished) = 1u;
+				break;
+			}
 
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
 			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
@@ -334,6 +364,7 @@ namespace sb
 				slot->start = 0ull;
 				slot->done = 0u;
 				slot->cross_end = 0u;
+				slot->sb_plus1 = 0u;
 			}
 			__syncwarp();
 			__threadfence_block();

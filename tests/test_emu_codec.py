@@ -193,3 +193,17 @@ def test_stream_encoder_ring_wrap_copy_superblocks_and_tail(T, n_sb, tail):
     assert api.kernel_launches() - l0 == 1  # the stream kernel alone
     assert got == want
     assert api.decompress(got, T, raw.size) == raw.tobytes()
+
+
+def test_stream_encoder_many_tiny_superblocks():
+    """cvector-style frame (one 256-element block per superblock) with ample room: hundreds of superblocks per CTA,
+    two tickets each -- exercises slot recycling, the global ticket counter and termination of idle warps."""
+    ctx = api.Context(block_shift=0)
+    raw = np.concatenate([raw_of(dists.make(n, 256 * 40, 4, seed=i)) for i, n in enumerate(("sparse_changes", "random", "lz_pairs", "const", "ramp_noise16"))]
+                         + [raw_of(dists.make("sorted", 77, 4))])
+    room = raw.size * 4 + 4096
+    want = port.compress(raw, 4, block_shift=0, dst_size=room)
+    l0 = api.kernel_launches()
+    assert ctx.compress(raw, 4, dst_size=room) == want
+    assert api.kernel_launches() - l0 == 1
+    assert api.decompress(want, 4, raw.size) == raw.tobytes()

@@ -289,3 +289,43 @@ def test_parallel_frame_index_on_adversarial_frames():
         assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), port.frame_index(frame, 4))
         if i == 0:
             assert ctx.index_accepted() == 1  # an ordinary frame is indexed by the parallel path, no serial fallback
+
+
+def _mixed(T, n_sb, seed, tail_elems):
+    per = 131072 // T
+    kinds = ["random", "ramp_noise16", "random", "lz_then_noise", "random", "random", "sparse_changes", "mostly_random_some_repeats", "const"]
+    parts = [raw_of(dists.make(kinds[(i + seed) % len(kinds)], per, T, seed=seed + i)) for i in range(n_sb)]
+    if tail_elems:
+        parts.append(raw_of(dists.make("random" if seed & 1 else "ramp_noise16", tail_elems, T, seed=seed)))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("T,n_sb,tail", [(4, 700, 255), (8, 450, 37), (2, 380, 0), (4, 33, 100)])
+def test_stream_encoder_mixed_superblocks(T, n_sb, tail):
+    """encode_stream_kernel (ample dst room -> every superblock through the barrier-free pipeline): long runs of
+    incompressible superblocks (ring wrap, waits for flushes, COPY), LZ blocks, constant data, a partial tail --
+    bit exact against the oracle, and the same bytes as the barrier kernel (STENOS_B200_LEGACY_ENCODER)."""
+    raw = _mixed(T, n_sb, seed=T + n_sb, tail_elems=tail)
+    room = raw.size + 300000
+    want = port.compress(raw, T, dst_size=room)
+    ctx = api.Context()
+    l0 = api.kernel_launches()
+    got = ctx.compress(raw, T, dst_size=room)
+    assert api.kernel_launches() - l0 == 1
+    assert got == want
+    assert ctx.decompress(got, T, raw.size) == raw.tobytes()
+    os.environ["STENOS_B200_LEGACY_ENCODER"] = "1"
+    try:
+        assert api.Context().compress(raw, T, dst_size=room) == want
+    finally:
+        del os.environ["STENOS_B200_LEGACY_ENCODER"]
+
+
+def test_stream_encoder_many_tiny_superblocks():
+    ctx = api.Context(block_shift=0)
+    raw = np.concatenate([raw_of(dists.make(n, 256 * 4000, 4, seed=i)) for i, n in enumerate(("sparse_changes", "random", "lz_pairs", "const", "ramp_noise16"))]
+                         + [raw_of(dists.make("sorted", 77, 4))])
+    room = raw.size * 2 + 4096
+    want = port.compress(raw, 4, block_shift=0, dst_size=room)
+    assert ctx.compress(raw, 4, dst_size=room) == want
+    assert api.decompress(want, 4, raw.size) == raw.tobytes()

@@ -3,7 +3,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from stenos_b200 import api, synth
+from stenos_b200 import api, capi, synth
+if os.environ.get("STENOS_B200_LIB"):
+    capi.use_library(capi.load(os.environ["STENOS_B200_LIB"]))
 
 def timeit(fn, n=5, w=2):
     for _ in range(w): fn()
