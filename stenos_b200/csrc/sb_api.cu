@@ -8,6 +8,7 @@
 // as well -- here through dlopen("libzstd.so.1").
 #include "sb_kernels.cuh"
 #include "sb_stream.cuh"
+#include "sb_decode_rows.cuh"
 #include "sb_filters.cuh"
 #include "../../include/stenos_b200.h"
 
@@ -124,6 +125,7 @@ struct stenos_context_s
 	DevBuf in, out, ctl, idx, scan;
 	bool serial_index = false; // tests: force the serial header walk
 	bool legacy_encoder = false; // tests: every superblock through encode_frame_kernel
+	bool legacy_decoder = false;
 	bool env_read = false;
 	bool index_ran = false;    // a parallel frame index was enqueued (its verdict is in scan.p)
 	unsigned long long* host_result = nullptr; // pinned, 4 words
@@ -146,6 +148,8 @@ struct stenos_context_s
 			// test hook: STENOS_B200_LEGACY_ENCODER=1 sends every superblock through encode_frame_kernel
 			const char* e = getenv("STENOS_B200_LEGACY_ENCODER");
 			legacy_encoder = e && e[0] == '1';
+			e = getenv("STENOS_B200_LEGACY_DECODER"); // likewise: one warp per superblock, lane per half row
+			legacy_decoder = e && e[0] == '1';
 			env_read = true;
 		}
 		if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
@@ -306,8 +310,16 @@ namespace
 	template<int T>
 	size_t launch_decode_T(stenos_context* ctx, const DecodeParams& P)
 	{
-		const unsigned grid = (P.n_sb + DECODE_WARPS - 1) / DECODE_WARPS;
-		STENOS_LAUNCH(decode_frame_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		if (ctx->legacy_decoder) {
+			const unsigned grid = (P.n_sb + DECODE_WARPS - 1) / DECODE_WARPS;
+			STENOS_LAUNCH(decode_frame_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		}
+		else {
+			// two superblocks per warp (one per half-warp, one lane per row)
+			const unsigned warps = (P.n_sb + 1) / 2;
+			const unsigned grid = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
+			STENOS_LAUNCH(decode_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * 512, ctx->stream(), P);
+		}
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
@@ -325,8 +337,15 @@ namespace
 	template<int T>
 	size_t launch_gather_T(stenos_context* ctx, const GatherParams& P)
 	{
-		const unsigned grid = (P.n + DECODE_WARPS - 1) / DECODE_WARPS;
-		STENOS_LAUNCH(gather_decode_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		if (ctx->legacy_decoder) {
+			const unsigned grid = (P.n + DECODE_WARPS - 1) / DECODE_WARPS;
+			STENOS_LAUNCH(gather_decode_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		}
+		else {
+			const unsigned warps = (P.n + 1) / 2;
+			const unsigned grid = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
+			STENOS_LAUNCH(gather_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * 512, ctx->stream(), P);
+		}
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}

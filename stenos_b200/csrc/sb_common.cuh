@@ -93,6 +93,25 @@ namespace sb
 
 	__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
+	// warms L1 with the line holding p: a load whose result is never used (no scoreboard wait follows it)
+	__device__ __forceinline__ void touch_l1(const void* p)
+	{
+#ifndef STENOS_EMU
+		uint32_t unused;
+		asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(unused) : "l"(p));
+#else
+		(void)p;
+#endif
+	}
+	__device__ __forceinline__ void prefetch_l2(const void* p)
+	{
+#ifndef STENOS_EMU
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+		(void)p;
+#endif
+	}
+
 	// 4x4 byte transpose: words a,b,c,d (one per element) -> p0..p3 (one per byte plane)
 	__device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3)
 	{

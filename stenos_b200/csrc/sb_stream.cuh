@@ -46,7 +46,7 @@ namespace sb
 		uint32_t ticket;
 		uint32_t flushed_q;   // superblocks [0, flushed_q) of this CTA are flushed, their slots reusable
 		uint32_t flushed_abs; // ring bytes below this absolute position are free
-		uint32_t finished;    // a ticket met a superblock past the end
+		uint32_t finished_q;  // first q of this CTA whose superblock is past the end (0xFFFFFFFF: not met yet)
 	};
 
 	template<int T, int NT>
@@ -150,6 +150,7 @@ namespace sb
 			reinterpret_cast<uint32_t*>(smem)[i] = 0u;
 		__syncthreads();
 		if (tid == 0) {
+			ctl->finished_q = 0xFFFFFFFFu;
 			slots[0].start = START_READY;
 			slots[0].sb_plus1 = blockIdx.x + 1u;
 		}
@@ -169,7 +170,7 @@ namespace sb
 			// the slot of q and the one of q + 1 (whose superblock and start are published from q) must be free
 			bool finished = false;
 			while ((int)(q - *v_flushed_q) >= (int)L::NSLOT - 1) {
-				if (*reinterpret_cast<volatile uint32_t*>(&ctl->finished)) { // nothing is left for this CTA: the slot will never come
+				if (q >= *reinterpret_cast<volatile uint32_t*>(&ctl->finished_q)) { // past this CTA's last superblock: the slot will never come
 					finished = true;
 					break;
 				}
@@ -179,14 +180,9 @@ namespace sb
 				break;
 			StreamSlot* slot = &slots[q % L::NSLOT];
 			uint32_t* chain = chains + (q % L::NSLOT) * L::PMAX;
-			if (j == 0 && lane == 0) {
-				// the next superblock of this CTA, one superblock ahead of its first use
-				const uint32_t nx = gridDim.x + atomicAdd(P.ticket + 1, 1u); // [1]: [0] belongs to encode_frame_kernel
-				*reinterpret_cast<volatile uint32_t*>(&slots[(q + 1u) % L::NSLOT].sb_plus1) = nx + 1u;
-			}
 			uint32_t s;
 			while ((s = *reinterpret_cast<volatile uint32_t*>(&slot->sb_plus1)) == 0u) {
-				if (*reinterpret_cast<volatile uint32_t*>(&ctl->finished)) {
+				if (q >= *reinterpret_cast<volatile uint32_t*>(&ctl->finished_q)) { // only tickets past the end may give up
 					s = 0xFFFFFFFFu;
 					break;
 				}
@@ -194,10 +190,17 @@ namespace sb
 			}
 			s -= 1u;
 			if (s >= P.n_stream) {
-				// superblocks are handed out in increasing order: every later ticket of this CTA is past the end too
+				// superblocks are handed out in increasing order: every ticket of this CTA from q on is past the end too
+				// (earlier ones are not, and must never give up)
 				if (lane == 0)
-					*reinterpret_cast<volatile uint32_t*>(&ctl->finished) = 1u;
+					atomicMin(&ctl->finished_q, q);
 				break;
+			}
+			if (j == 0 && lane == 0) {
+				// the next superblock of this CTA, one superblock ahead of its first use.  Asked for only once this
+				// one is known, so that a CTA's superblocks are numbered in increasing order of q.
+				const uint32_t nx = gridDim.x + atomicAdd(P.ticket + 1, 1u); // [1]: [0] belongs to encode_frame_kernel
+				*reinterpret_cast<volatile uint32_t*>(&slots[(q + 1u) % L::NSLOT].sb_plus1) = nx + 1u;
 			}
 
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;

@@ -207,3 +207,21 @@ def test_stream_encoder_many_tiny_superblocks():
     assert ctx.compress(raw, 4, dst_size=room) == want
     assert api.kernel_launches() - l0 == 1
     assert api.decompress(want, 4, raw.size) == raw.tobytes()
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_row_decoder_every_distribution(T):
+    """decode_pairs_kernel's lane-per-row path only takes blocks that lie a worst-case block before the end of the
+    buffer: put every distribution in front of an incompressible tail so that its blocks are decoded there, and
+    check it against the barrier-free decoder's predecessor (STENOS_B200_LEGACY_DECODER) as well."""
+    import os
+    tail = raw_of(dists.make("random", 256 * 3, T, seed=77))
+    for name in dists.names():
+        raw = np.concatenate([raw_of(dists.make(name, 256 * 5, T, seed=11)), tail])
+        c = port.compress(raw, T)
+        assert api.decompress(c, T, raw.size) == raw.tobytes(), name
+    os.environ["STENOS_B200_LEGACY_DECODER"] = "1"
+    try:
+        assert api.Context().decompress(c, T, raw.size) == raw.tobytes()
+    finally:
+        del os.environ["STENOS_B200_LEGACY_DECODER"]
