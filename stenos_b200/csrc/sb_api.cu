@@ -122,7 +122,7 @@ struct stenos_context_s
 	size_t superblock = 0;
 	int shift = 0;
 	// scratch
-	DevBuf in, out, ctl, idx, scan;
+	DevBuf in, out, ctl, idx, scan, dtk;
 	bool serial_index = false; // tests: force the serial header walk
 	bool legacy_encoder = false; // tests: every superblock through encode_frame_kernel
 	bool legacy_decoder = false;
@@ -206,6 +206,7 @@ struct stenos_context_s
 		ctl.release();
 		idx.release();
 		scan.release();
+		dtk.release();
 		if (host_result)
 			cudaFreeHost(host_result);
 		host_result = nullptr;
@@ -315,10 +316,23 @@ namespace
 			STENOS_LAUNCH(decode_frame_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
 		}
 		else {
-			// two superblocks per warp (one per half-warp, one lane per row)
+			// two superblocks per warp (one per half-warp, one lane per row); persistent warps, work by ticket
+			if (!ctx->dtk.reserve(16))
+				return STENOS_ERROR_ALLOC;
+			cudaMemsetAsync(ctx->dtk.p, 0, 16, ctx->stream());
+			DecodeParams Q = P;
+			Q.ticket = reinterpret_cast<unsigned long long*>(ctx->dtk.p);
+			int per_sm = 1;
+#ifndef STENOS_EMU
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_pairs_kernel<T>, DECODE2_WARPS * 32, DECODE2_WARPS * 512) != cudaSuccess || per_sm < 1) {
+				cudaGetLastError();
+				per_sm = 1;
+			}
+#endif
 			const unsigned warps = (P.n_sb + 1) / 2;
-			const unsigned grid = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
-			STENOS_LAUNCH(decode_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * 512, ctx->stream(), P);
+			const unsigned need = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
+			const unsigned grid = std::min<unsigned>(need, (unsigned)(ctx->sm_count * per_sm));
+			STENOS_LAUNCH(decode_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * 512, ctx->stream(), Q);
 		}
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
@@ -760,6 +774,7 @@ namespace
 			d_dst = ctx->out.p;
 		}
 		DecodeParams P;
+		P.ticket = nullptr;
 		P.src = d_src;
 		P.src_size = size;
 		P.dst = d_dst;
@@ -1151,6 +1166,7 @@ size_t stenos_b200_decompress_range_async(stenos_context* ctx, const void* d_fra
 			return STENOS_ERROR_INVALID_PARAMETER;
 		cudaMemsetAsync(d_result, 0, 16, ctx->stream());
 		DecodeParams P;
+		P.ticket = nullptr;
 		P.src = (const uint8_t*)d_frame;
 		P.src_size = frame_bytes;
 		P.dst = (uint8_t*)d_dst;
@@ -1197,6 +1213,7 @@ size_t stenos_b200_decompress_async(stenos_context* ctx, const void* d_src, size
 			offs = built;
 		}
 		DecodeParams P;
+		P.ticket = nullptr;
 		P.src = (const uint8_t*)d_src;
 		P.src_size = bytes;
 		P.dst = (uint8_t*)d_dst;

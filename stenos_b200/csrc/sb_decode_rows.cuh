@@ -443,27 +443,40 @@ namespace sb
 		return err;
 	}
 
-	constexpr int DECODE2_WARPS = 4;
+#ifndef DECODE2_WARPS_PER_CTA
+#define DECODE2_WARPS_PER_CTA 4
+#endif
+#ifndef DECODE2_MIN_CTAS
+#define DECODE2_MIN_CTAS 6
+#endif
+	constexpr int DECODE2_WARPS = DECODE2_WARPS_PER_CTA;
 
-	// frame decoder: warp w of the grid takes superblocks 2w and 2w + 1
+	// frame decoder: persistent warps; a warp takes the next two superblocks (one per half-warp) by ticket, so
+	// streams of very different cost (constant data next to noisy data) do not leave SMs idle behind a slow CTA
 	template<int T>
-	__global__ void __launch_bounds__(DECODE2_WARPS * 32) decode_pairs_kernel(DecodeParams P)
+	__global__ void __launch_bounds__(DECODE2_WARPS * 32, DECODE2_MIN_CTAS) decode_pairs_kernel(DecodeParams P)
 	{
 		STENOS_DYN_SMEM(uint8_t, smem);
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		uint16_t* lz_scratch = reinterpret_cast<uint16_t*>(smem) + 256 * warp;
-		const uint32_t i = 2u * (blockIdx.x * DECODE2_WARPS + warp) + (uint32_t)(lane >> 4);
-		if (i - (uint32_t)(lane >> 4) >= P.n_sb)
-			return;
-		const bool valid = i < P.n_sb;
-		const uint32_t s = P.first_sb + (valid ? i : 0u);
-		const uint64_t doff = (uint64_t)s * P.sb_bytes;
-		const uint32_t dsize = (uint32_t)min((uint64_t)P.sb_bytes, P.total - doff); // remainder 0 = full superblock (appendix C1)
-		const bool last = (doff + dsize == P.total);
-		const uint32_t bad = decode_superblock_pair<T>(P.src, P.src_size, P.sb_offsets[s], dsize, P.dst + (doff - P.dst_origin), valid, P.skip_zstd_tail && last,
-							       lz_scratch, lane);
-		if (bad && valid && (lane & 15) == 0)
-			atomicOr(&P.result[1], (unsigned long long)bad);
+		for (;;) {
+			uint32_t w = 0;
+			if (lane == 0)
+				w = (uint32_t)atomicAdd(P.ticket, 1ull);
+			w = __shfl_sync(FULL, w, 0);
+			if (2ull * w >= (unsigned long long)P.n_sb)
+				break;
+			const uint32_t i = 2u * w + (uint32_t)(lane >> 4);
+			const bool valid = i < P.n_sb;
+			const uint32_t s = P.first_sb + (valid ? i : 0u);
+			const uint64_t doff = (uint64_t)s * P.sb_bytes;
+			const uint32_t dsize = (uint32_t)min((uint64_t)P.sb_bytes, P.total - doff); // remainder 0 = full superblock (appendix C1)
+			const bool last = (doff + dsize == P.total);
+			const uint32_t bad = decode_superblock_pair<T>(P.src, P.src_size, P.sb_offsets[s], dsize, P.dst + (doff - P.dst_origin), valid, P.skip_zstd_tail && last,
+								       lz_scratch, lane);
+			if (bad && valid && (lane & 15) == 0)
+				atomicOr(&P.result[1], (unsigned long long)bad);
+		}
 	}
 
 	// stenos::cvector random access: one half-warp per requested bucket (cvector.hpp:2879 -> :1862-1883)

@@ -672,6 +672,7 @@ namespace sb
 		unsigned long long* result;           // [1] error bits
 		uint32_t skip_zstd_tail;              // 1: a code-2 (Zstd) final superblock is left to the host
 		uint64_t dst_origin; // decompressed offset that dst[0] corresponds to (multi-GPU segments)
+		unsigned long long* ticket; // decode_pairs_kernel: zero initialised work counter
 	};
 
 	constexpr int DECODE_WARPS = 4;
