@@ -304,7 +304,7 @@ def main():
                    "parallelism": "superblock ranges per GPU, segment sizes all-gathered" if world > 1 else "1 GPU"},
         "decompress_GBps": frame_bytes / (d_step_ms * 1e-3) / 1e9, "decompress_ms_per_step": d_step_ms,
         "ratio": nbytes / csize, "compressed_bytes_per_gpu": csize,
-        "roofline": {"bound": "hbm", "kernel": "encode_stream_kernel<4,512>", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "encode_stream_kernel<4,640>", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
         "roofline_decompress": {"bound": "hbm", "kernel": "decode_pairs_kernel<4> (+ index_scan/merge/fill: the step walks the frame headers on the device)", "achieved": alg_bytes / (float(np.mean(d_per)) * 1e-3) / 1e9, "peak": peak,

@@ -103,6 +103,20 @@ namespace sb
 		(void)p;
 #endif
 	}
+	// Asks for the line holding p to be brought into L1 without tying up a register or a scoreboard: an asynchronous
+	// 4-byte copy (LDGSTS, cached at all levels) into a scratch word of shared memory that nobody reads.  A load into
+	// an unused register (touch_l1) is only half asynchronous: the register's next writer waits for it.
+	__device__ __forceinline__ void prefetch_l1_async(const void* p, void* smem_scratch_word)
+	{
+#ifndef STENOS_EMU
+		const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_scratch_word);
+		const uintptr_t g = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3;
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g) : "memory");
+#else
+		(void)p;
+		(void)smem_scratch_word;
+#endif
+	}
 	__device__ __forceinline__ void prefetch_l2(const void* p)
 	{
 #ifndef STENOS_EMU

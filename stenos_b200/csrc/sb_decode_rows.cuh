@@ -275,8 +275,16 @@ namespace sb
 		}
 		uint4* dst = reinterpret_cast<uint4*>(block + (size_t)r * 16 * T);
 #pragma unroll
-		for (int i = 0; i < T; ++i)
-			dst[i] = make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+		for (int i = 0; i < T; ++i) {
+			const uint4 v = make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+#if defined(DECODE_STORE_CS) && !defined(STENOS_EMU)
+			__stcs(dst + i, v); // the output is written once and never read here: keep it out of the way of the stream's lines
+#elif defined(DECODE_STORE_CG) && !defined(STENOS_EMU)
+			__stcg(dst + i, v);
+#else
+			dst[i] = v;
+#endif
+		}
 	}
 
 	// worst case of a plane coded block: kinds + T planes of 8 header bytes, 16 mins and 16 rows of 18 bytes
@@ -333,7 +341,7 @@ namespace sb
 	// (of that half) into dsize bytes at `out`.  valid: the half has a superblock.  Returns the half's device error bits.
 	template<int T>
 	__device__ __forceinline__ uint32_t decode_superblock_pair(const uint8_t* src, uint64_t src_size, uint64_t at, uint32_t dsize, uint8_t* out, bool valid,
-								   bool allow_zstd_tail, uint16_t* lz_scratch, int lane)
+								   bool allow_zstd_tail, uint16_t* lz_scratch, int lane, void* scratch_word = nullptr)
 	{
 		constexpr uint32_t BLOCK = T * 256u;
 		constexpr uint32_t HS = (T + 1) / 2;
@@ -403,8 +411,16 @@ namespace sb
 				// the stream is read front to back: keep the lines a few blocks ahead on their way to L1
 				if (fast && r < DECODE_AHEAD_LINES) {
 					const uint8_t* ahead = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(q) + DECODE_AHEAD_BYTES + 128u * r) & ~(uintptr_t)127);
-					if (ahead + 128 <= lim)
+					if (ahead + 128 <= lim) {
+#ifdef DECODE_TOUCH_SYNC
 						touch_l1(ahead);
+#else
+						if (scratch_word)
+							prefetch_l1_async(ahead, scratch_word);
+						else
+							touch_l1(ahead);
+#endif
+					}
 				}
 				const uint32_t c = decode_block_rows<T>(q, fast, r, hsh, o);
 				if (fast)
@@ -459,6 +475,7 @@ namespace sb
 		STENOS_DYN_SMEM(uint8_t, smem);
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		uint16_t* lz_scratch = reinterpret_cast<uint16_t*>(smem) + 256 * warp;
+		void* scratch_word = smem + DECODE2_WARPS * 512 + 4 * threadIdx.x; // target of the asynchronous L1 prefetches, never read
 		for (;;) {
 			uint32_t w = 0;
 			if (lane == 0)
@@ -473,7 +490,7 @@ namespace sb
 			const uint32_t dsize = (uint32_t)min((uint64_t)P.sb_bytes, P.total - doff); // remainder 0 = full superblock (appendix C1)
 			const bool last = (doff + dsize == P.total);
 			const uint32_t bad = decode_superblock_pair<T>(P.src, P.src_size, P.sb_offsets[s], dsize, P.dst + (doff - P.dst_origin), valid, P.skip_zstd_tail && last,
-								       lz_scratch, lane);
+								       lz_scratch, lane, scratch_word);
 			if (bad && valid && (lane & 15) == 0)
 				atomicOr(&P.result[1], (unsigned long long)bad);
 		}

@@ -208,6 +208,28 @@ namespace sb
 			const uint32_t nfull = in_bytes / L::BLOCK, rem = in_bytes - nfull * L::BLOCK;
 			const uint32_t npairs = (nfull + 1u) >> 1;
 
+#ifndef STREAM_NO_PREFETCH
+			// The pair NWARPS tickets ahead (roughly this warp's next one) starts its way from HBM to L2 now: its
+			// loads then meet L2 latency instead of DRAM latency.  A wrong guess costs nothing but the request.
+			{
+				uint32_t jj = j + L::NWARPS;
+				const uint8_t* pf = nullptr;
+				if (jj < npairs)
+					pf = in + (size_t)(2u * jj) * L::BLOCK;
+				else {
+					jj -= PT;
+					const uint32_t s1 = *reinterpret_cast<volatile uint32_t*>(&slots[(q + 1u) % L::NSLOT].sb_plus1);
+					if (s1 != 0u && s1 - 1u < P.n_stream && jj < PT)
+						pf = P.src + (uint64_t)(s1 - 1u) * P.sb_bytes + (size_t)(2u * jj) * L::BLOCK;
+				}
+				if (pf != nullptr && lane < 4 * T) {
+					const uint8_t* a = pf + 128u * (uint32_t)lane;
+					if (a < P.src + P.bytes)
+						prefetch_l2(a);
+				}
+			}
+#endif
+
 			// sizes are final -> stream offset (look-back), ring position, room in the ring
 			uint32_t abs0 = 0, excl = 0;
 			auto place_pair = [&](uint32_t sz2) {
