@@ -1366,7 +1366,7 @@ namespace
 		const uint64_t nchunks = (bytes + chunk - 1) / chunk;
 		auto run_delta = [&](const FilterParams& Q, bool inverse) {
 			if (inverse) {
-				STENOS_LAUNCH(delta_inv_kernel, dim3((unsigned)(nchunks * 4)), dim3(FILTER_THREADS), 64, st, Q);
+				STENOS_LAUNCH(delta_inv_kernel, dim3((unsigned)(nchunks * 4)), dim3(DELTA_INV_THREADS), 128, st, Q);
 			}
 			else {
 				const uint64_t groups = nchunks * ((chunk + 15) / 16);

@@ -13,6 +13,7 @@
 // elements with 128-bit accesses on both sides.
 #pragma once
 #include "sb_common.cuh"
+#include "sb_decode_rows.cuh" // sad4_acc, prefix16
 
 namespace sb
 {
@@ -278,8 +279,12 @@ namespace sb
 			dst[i] = delta_stream_start(i, cb) ? src[i] : (uint8_t)(src[i] - src[i - 1]);
 	}
 
-	// inverse delta: one CTA per (chunk, stream); the stream is scanned tile by tile with a running carry
-	__global__ void __launch_bounds__(FILTER_THREADS) delta_inv_kernel(FilterParams P)
+	// inverse delta (delta.cpp:230-267): one CTA per (chunk, stream); the stream is scanned tile by tile (16 bytes per
+	// thread, one 128-bit load and store each) with a running carry.  Per tile: byte sums of the 16-byte groups
+	// (VABSDIFF4), one CTA-wide scan of them, then the in-group prefix sums on top of the group's carry
+	// (prefix16: 16-bit lanes, one IMAD per word).
+	constexpr int DELTA_INV_THREADS = 1024;
+	__global__ void __launch_bounds__(DELTA_INV_THREADS) delta_inv_kernel(FilterParams P)
 	{
 		STENOS_DYN_SMEM(uint32_t, warp_sums);
 		const uint64_t c = blockIdx.x >> 2;
@@ -300,17 +305,29 @@ namespace sb
 		const uint8_t* src = P.src + c * P.chunk;
 		uint8_t* dst = P.dst + c * P.chunk;
 		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		const bool aligned = (((uintptr_t)(src + lo) | (uintptr_t)(dst + lo)) & 15u) == 0;
 		uint32_t carry = 0;
-		for (uint64_t t0 = lo; t0 < hi; t0 += FILTER_THREADS * 16) {
+		for (uint64_t t0 = lo; t0 < hi; t0 += (uint64_t)DELTA_INV_THREADS * 16) {
 			const uint64_t i0 = t0 + (uint64_t)tid * 16;
-			uint8_t v[16];
+			const bool full = aligned && i0 + 16 <= hi;
+			uint32_t x[4] = { 0u, 0u, 0u, 0u };
+			if (full) {
+				const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
+				x[0] = v.x;
+				x[1] = v.y;
+				x[2] = v.z;
+				x[3] = v.w;
+			}
+			else {
+#pragma unroll
+				for (int k = 0; k < 16; ++k)
+					if (i0 + k < hi)
+						x[k >> 2] |= (uint32_t)src[i0 + k] << (8 * (k & 3));
+			}
 			uint32_t sum = 0;
 #pragma unroll
-			for (int k = 0; k < 16; ++k) {
-				v[k] = (i0 + k < hi) ? src[i0 + k] : (uint8_t)0;
-				sum += v[k];
-				v[k] = (uint8_t)sum;
-			}
+			for (int j = 0; j < 4; ++j)
+				sum = sad4_acc(x[j], 0u, sum);
 			// CTA-wide exclusive scan of the per-thread sums (mod 256)
 			uint32_t incl = sum;
 #pragma unroll
@@ -322,19 +339,21 @@ namespace sb
 			if (lane == 31)
 				warp_sums[warp] = incl;
 			__syncthreads();
-			uint32_t wpre = 0, tot = 0;
-			for (int i = 0; i < FILTER_THREADS / 32; ++i) {
-				const uint32_t ws = warp_sums[i];
-				if (i < warp)
-					wpre += ws;
-				tot += ws;
-			}
+			const uint32_t ws = warp_sums[lane]; // DELTA_INV_THREADS / 32 == 32 warps
+			const uint32_t wpre = __reduce_add_sync(FULL, lane < warp ? ws : 0u);
+			const uint32_t tot = __reduce_add_sync(FULL, ws);
 			__syncthreads();
-			const uint32_t add = carry + wpre + (incl - sum);
+			const uint32_t add = (carry + wpre + (incl - sum)) & 0xFFu;
+			uint32_t o[4];
+			prefix16(x, 0u, add, o);
+			if (full)
+				*reinterpret_cast<uint4*>(dst + i0) = make_uint4(o[0], o[1], o[2], o[3]);
+			else {
 #pragma unroll
-			for (int k = 0; k < 16; ++k)
-				if (i0 + k < hi)
-					dst[i0 + k] = (uint8_t)(v[k] + add);
+				for (int k = 0; k < 16; ++k)
+					if (i0 + k < hi)
+						dst[i0 + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+			}
 			carry = (carry + tot) & 0xFFu;
 		}
 	}
