@@ -1321,12 +1321,15 @@ namespace
 	void launch_shuffle_T(stenos_context* ctx, const FilterParams& P, bool inverse)
 	{
 		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
-		const uint64_t groups = nchunks * ((P.chunk / T + 15) / 16 + 1);
-		const unsigned grid = (unsigned)((groups + FILTER_THREADS - 1) / FILTER_THREADS);
+		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
+		const uint64_t ctas_per_chunk = (groups_per_chunk + FILTER_THREADS - 1) / FILTER_THREADS;
+		FilterParams Q = P;
+		Q.chunk_in_y = nchunks <= 65535 ? 1u : 0u; // grid.y is limited to 65535; one of the two always fits
+		const dim3 grid = Q.chunk_in_y ? dim3((unsigned)ctas_per_chunk, (unsigned)nchunks) : dim3((unsigned)nchunks, (unsigned)ctas_per_chunk);
 		if (inverse)
-			STENOS_LAUNCH(unshuffle_kernel<T>, dim3(grid), dim3(FILTER_THREADS), 0, ctx->stream(), P);
+			STENOS_LAUNCH(unshuffle_kernel<T>, grid, dim3(FILTER_THREADS), 0, ctx->stream(), Q);
 		else
-			STENOS_LAUNCH(shuffle_kernel<T>, dim3(grid), dim3(FILTER_THREADS), 0, ctx->stream(), P);
+			STENOS_LAUNCH(shuffle_kernel<T>, grid, dim3(FILTER_THREADS), 0, ctx->stream(), Q);
 		++g_launches;
 	}
 
@@ -1363,6 +1366,7 @@ namespace
 		P.bytes = bytes;
 		P.chunk = chunk;
 		P.with_delta = with_delta ? 1u : 0u;
+		P.chunk_in_y = 0;
 		const uint64_t nchunks = (bytes + chunk - 1) / chunk;
 		auto run_delta = [&](const FilterParams& Q, bool inverse) {
 			if (inverse) {

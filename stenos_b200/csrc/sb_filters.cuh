@@ -24,6 +24,7 @@ namespace sb
 		uint64_t bytes; // total
 		uint64_t chunk; // bytes per independently filtered piece (last one may be shorter)
 		uint32_t with_delta; // shuffle: also apply the byte delta (fused); unshuffle: unused
+		uint32_t chunk_in_y; // grid layout of the transposes: 0: x = chunk, y = groups of a chunk; 1: the other way round
 	};
 
 	// position i of a chunk of `bytes` bytes starts a delta stream? (delta.cpp:42-70)
@@ -124,6 +125,11 @@ namespace sb
 		r.w = __vsub4(v.w, prev_bytes(v.z, v.w));
 		return r;
 	}
+	__device__ __forceinline__ uint32_t byte16(const uint4& v, uint32_t idx)
+	{
+		const uint32_t a = idx < 4 ? v.x : idx < 8 ? v.y : idx < 12 ? v.z : v.w;
+		return (a >> ((idx & 3u) * 8u)) & 0xFFu;
+	}
 	__device__ __forceinline__ void set_byte16(uint4& v, uint32_t idx, uint32_t b)
 	{
 		uint32_t* a = idx < 4 ? &v.x : idx < 8 ? &v.y : idx < 12 ? &v.z : &v.w;
@@ -137,15 +143,11 @@ namespace sb
 	template<int T>
 	__global__ void __launch_bounds__(FILTER_THREADS) shuffle_kernel(FilterParams P)
 	{
-		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
-		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
-		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
-		const uint64_t c = g / groups_per_chunk;
-		if (c >= nchunks)
-			return;
+		// grid: x = chunk, y * FILTER_THREADS + thread = group of 16 elements inside the chunk (+ one group for the leftover bytes)
+		const uint64_t c = P.chunk_in_y ? blockIdx.y : blockIdx.x;
 		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk); // bytes of this chunk
 		const uint64_t n = cb / T;                                // elements
-		const uint64_t j0 = (g - c * groups_per_chunk) * 16;      // first element of this thread
+		const uint64_t j0 = ((uint64_t)(P.chunk_in_y ? blockIdx.x : blockIdx.y) * FILTER_THREADS + threadIdx.x) * 16; // first element of this thread
 		const uint8_t* src = P.src + c * P.chunk;
 		uint8_t* dst = P.dst + c * P.chunk;
 		if (j0 >= n) {
@@ -174,30 +176,49 @@ namespace sb
 			}
 			uint4 pl[T];
 			transpose16<T>(w, pl);
+			// fused delta (delta.cpp:30-71 on the transposed chunk): the byte before plane k's 16 bytes is byte k of the
+			// element before j0 -- or, for the first group, byte k - 1 of the chunk's last element.  One element load
+			// (the neighbour thread has just fetched the line), not T byte loads.
+			uint32_t pe[2] = { 0u, 0u };
+			uint64_t q1 = ~0ull, q2 = ~0ull, q3 = ~0ull; // starts of the quarter streams 1..3 (chunk offsets)
+			if (P.with_delta) {
+				const uint8_t* e = src + (j0 ? j0 - 1 : n - 1) * T;
+				if (T == 2)
+					pe[0] = *reinterpret_cast<const uint16_t*>(e);
+				else if (T == 4)
+					pe[0] = *reinterpret_cast<const uint32_t*>(e);
+				else {
+					const uint2 t = *reinterpret_cast<const uint2*>(e);
+					pe[0] = t.x;
+					pe[1] = t.y;
+				}
+				if (j0 == 0) { // byte k - 1 of the last element; nothing before plane 0
+					pe[1] = T == 8 ? __funnelshift_l(pe[0], pe[1], 8) : 0u;
+					pe[0] <<= 8;
+				}
+				if (cb > 2048) {
+					q1 = cb / 4;
+					q2 = 2u * q1;
+					q3 = 3u * q1;
+				}
+			}
 #pragma unroll
 			for (int k = 0; k < T; ++k) {
 				uint4 v = pl[k];
 				if (P.with_delta) {
-					// byte before position k*n + j0 of the transposed chunk
-					const uint64_t i0 = (uint64_t)k * n + j0;
-					uint32_t before = 0;
-					if (j0)
-						before = src[(j0 - 1) * T + k];
-					else if (k)
-						before = src[(n - 1) * T + (k - 1)];
+					const uint64_t i0 = (uint64_t)k * n + j0; // chunk offset of the plane's 16 bytes
+					const uint32_t before = (pe[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+					const uint4 raw = v;
 					v = delta16(v, before);
 					// stream starts keep the raw byte
-					if (cb > 2048) {
-						const uint64_t q = cb / 4;
-#pragma unroll
-						for (int m = 0; m < 4; ++m) {
-							const uint64_t st = (uint64_t)m * q;
-							if (st >= i0 && st < i0 + 16)
-								set_byte16(v, (uint32_t)(st - i0), src[(st - (uint64_t)k * n) * T + k]);
-						}
-					}
-					else if (i0 == 0)
-						set_byte16(v, 0, src[0]);
+					if (i0 == 0)
+						set_byte16(v, 0, raw.x & 0xFFu);
+					if (q1 - i0 < 16ull)
+						set_byte16(v, (uint32_t)(q1 - i0), byte16(raw, (uint32_t)(q1 - i0)));
+					if (q2 - i0 < 16ull)
+						set_byte16(v, (uint32_t)(q2 - i0), byte16(raw, (uint32_t)(q2 - i0)));
+					if (q3 - i0 < 16ull)
+						set_byte16(v, (uint32_t)(q3 - i0), byte16(raw, (uint32_t)(q3 - i0)));
 				}
 				*reinterpret_cast<uint4*>(dst + (uint64_t)k * n + j0) = v;
 			}
@@ -221,15 +242,10 @@ namespace sb
 	template<int T>
 	__global__ void __launch_bounds__(FILTER_THREADS) unshuffle_kernel(FilterParams P)
 	{
-		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
-		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
-		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
-		const uint64_t c = g / groups_per_chunk;
-		if (c >= nchunks)
-			return;
+		const uint64_t c = P.chunk_in_y ? blockIdx.y : blockIdx.x;
 		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
 		const uint64_t n = cb / T;
-		const uint64_t j0 = (g - c * groups_per_chunk) * 16;
+		const uint64_t j0 = ((uint64_t)(P.chunk_in_y ? blockIdx.x : blockIdx.y) * FILTER_THREADS + threadIdx.x) * 16;
 		const uint8_t* src = P.src + c * P.chunk;
 		uint8_t* dst = P.dst + c * P.chunk;
 		if (j0 >= n) {
