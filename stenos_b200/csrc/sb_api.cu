@@ -1396,16 +1396,40 @@ namespace
 				break;
 			case OP_UNSHUFFLE:
 				if (with_delta) {
-					// delta_inv into scratch, then unshuffle (stenos.cpp:722-724)
-					if (!ctx->idx.reserve(bytes + 16))
-						return STENOS_ERROR_ALLOC;
-					FilterParams A = P;
-					A.dst = ctx->idx.p;
-					run_delta(A, true);
-					FilterParams B = P;
-					B.src = ctx->idx.p;
-					B.with_delta = 0;
-					run_shuffle(B, true);
+					// delta_inv, then unshuffle (stenos.cpp:722-724).  Whole chunks that are a multiple of 16 elements go
+					// through the fused kernel (2N of traffic); a ragged tail chunk, tiny chunks and unaligned buffers
+					// through delta_inv into scratch + unshuffle (4N).
+					uint64_t fused_chunks = 0;
+					if (supported_T(T) && chunk > 2048 && chunk % (16 * T) == 0 && (((uintptr_t)d_src | (uintptr_t)d_dst) & 15u) == 0)
+						fused_chunks = bytes / chunk;
+					if (fused_chunks) {
+						FilterParams F = P;
+						F.bytes = fused_chunks * chunk;
+						switch (T) {
+							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
+							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
+							case 8: STENOS_LAUNCH(unshuffle_delta_kernel<8>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
+						}
+						++g_launches;
+					}
+					const uint64_t done = fused_chunks * chunk;
+					if (done < bytes) {
+						const uint64_t rest = bytes - done;
+						if (!ctx->idx.reserve(rest + 16))
+							return STENOS_ERROR_ALLOC;
+						FilterParams A = P;
+						A.src = P.src + done;
+						A.bytes = rest;
+						A.dst = ctx->idx.p;
+						const uint64_t rchunks = (rest + chunk - 1) / chunk;
+						STENOS_LAUNCH(delta_inv_kernel, dim3((unsigned)(rchunks * 4)), dim3(DELTA_INV_THREADS), 128, st, A);
+						++g_launches;
+						FilterParams B = A;
+						B.src = ctx->idx.p;
+						B.dst = P.dst + done;
+						B.with_delta = 0;
+						run_shuffle(B, true);
+					}
 				}
 				else
 					run_shuffle(P, true);

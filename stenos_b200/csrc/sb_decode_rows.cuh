@@ -294,6 +294,15 @@ namespace sb
 		static constexpr uint32_t READ = (T + 1) / 2 + T * 312u + 24u;
 	};
 
+	// The affine maps last = a * prev + c (a in {0, 1}) of TWO planes, one per 16-bit lane (c in bits 0..7, a in bit 8):
+	// x := x o y (apply y first), lane wise, without any carry between the lanes
+	__device__ __forceinline__ uint32_t compose_maps2(uint32_t x, uint32_t y)
+	{
+		const uint32_t m = (x >> 8) & 0x00010001u;
+		const uint32_t sel = (m << 8) - m; // 0x00FF in the lanes whose a is 1
+		return (((x & 0x00FF00FFu) + (y & sel)) & 0x00FF00FFu) | (x & y & 0x01000100u);
+	}
+
 #ifndef DECODE_ROWS_TWO_PHASE
 	// One full plane-coded block per half-warp: p -> 256 elements at out.  live: the lane's half has a block here.
 	// Returns the bytes consumed (uniform over the half-warp), 0xFFFFFFFF for an invalid plane kind.
@@ -339,15 +348,6 @@ namespace sb
 	}
 
 #else
-	// The affine maps last = a * prev + c (a in {0, 1}) of TWO planes, one per 16-bit lane (c in bits 0..7, a in bit 8):
-	// x := x o y (apply y first), lane wise, without any carry between the lanes
-	__device__ __forceinline__ uint32_t compose_maps2(uint32_t x, uint32_t y)
-	{
-		const uint32_t m = (x >> 8) & 0x00010001u;
-		const uint32_t sel = (m << 8) - m; // 0x00FF in the lanes whose a is 1
-		return (((x & 0x00FF00FFu) + (y & sel)) & 0x00FF00FFu) | (x & y & 0x01000100u);
-	}
-
 	// One full plane-coded block per half-warp: p -> 256 elements at out.  live: the lane's half has a block here.
 	// Returns the bytes consumed (uniform over the half-warp), 0xFFFFFFFF for an invalid plane kind.
 	//

@@ -373,4 +373,164 @@ namespace sb
 			carry = (carry + tot) & 0xFFu;
 		}
 	}
+
+	// ------------------------------------------------------------------------------------------
+	// unshuffle with the inverse delta fused in (stenos.cpp:711-725: delta_inv, then unshuffle): one CTA per chunk
+	// walks it tile by tile (16 elements per thread); every byte plane carries its own running prefix sum, since for a
+	// fixed plane the positions k * n + j of the transposed chunk grow with j.  HBM traffic 2N instead of the 4N of
+	// delta_inv into scratch + unshuffle.  Where a quarter stream starts (delta.cpp:42-70) the sum restarts: a group
+	// is an affine map last = a * prev + c with a = 0 if it holds a restart, and the CTA scans maps, two planes per
+	// register (compose_maps2).  Requires cb % (16 * T) == 0 and 16-byte aligned chunks (the host checks).
+	// ------------------------------------------------------------------------------------------
+	constexpr int UNSHUFFLE_DELTA_THREADS = 512;
+	template<int T>
+	__global__ void __launch_bounds__(UNSHUFFLE_DELTA_THREADS) unshuffle_delta_kernel(FilterParams P)
+	{
+		constexpr int NW = UNSHUFFLE_DELTA_THREADS / 32;
+		constexpr int NP = T / 2; // plane pairs
+		STENOS_DYN_SMEM(uint32_t, warp_maps_raw); // [NP][NW]
+		uint32_t (*warp_maps)[NW] = reinterpret_cast<uint32_t (*)[NW]>(warp_maps_raw);
+		const uint64_t c = blockIdx.x;
+		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
+		const uint64_t n = cb / T;
+		const uint8_t* src = P.src + c * P.chunk;
+		uint8_t* dst = P.dst + c * P.chunk;
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		const uint64_t q1 = cb > 2048 ? cb / 4 : ~0ull; // starts of the quarter streams 1..3
+		const uint64_t q2 = cb > 2048 ? 2 * (cb / 4) : ~0ull, q3 = cb > 2048 ? 3 * (cb / 4) : ~0ull;
+		uint32_t run[NP]; // running carries (c only), two planes per register
+#pragma unroll
+		for (int pp = 0; pp < NP; ++pp)
+			run[pp] = 0u;
+		if (T == 8) {
+			// n = q / 2: an odd plane starts in the middle of a quarter stream, on top of the sum of the plane before it.
+			// One extra read of the even planes (they are read again below, from L2).
+			uint32_t s[NP];
+#pragma unroll
+			for (int e = 0; e < NP; ++e)
+				s[e] = 0u;
+			for (uint64_t j = (uint64_t)tid * 16; j < n; j += (uint64_t)UNSHUFFLE_DELTA_THREADS * 16) {
+#pragma unroll
+				for (int e = 0; e < NP; ++e) {
+					const uint4 v = *reinterpret_cast<const uint4*>(src + (uint64_t)(2 * e) * n + j);
+					s[e] = sad4_acc(v.x, 0u, sad4_acc(v.y, 0u, sad4_acc(v.z, 0u, sad4_acc(v.w, 0u, s[e]))));
+				}
+			}
+#pragma unroll
+			for (int e = 0; e < NP; ++e) {
+				const uint32_t ws = __reduce_add_sync(FULL, s[e]);
+				if (lane == 0)
+					warp_maps[e][warp] = ws;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int e = 0; e < NP; ++e) {
+				const uint32_t tot = __reduce_add_sync(FULL, lane < NW ? warp_maps[e][lane] : 0u);
+				run[e] = (tot & 0xFFu) << 16; // planes 2e (starts a stream: 0) and 2e + 1
+			}
+			__syncthreads();
+		}
+		for (uint64_t t0 = 0; t0 < n; t0 += (uint64_t)UNSHUFFLE_DELTA_THREADS * 16) {
+			const uint64_t j0 = t0 + (uint64_t)tid * 16;
+			const bool live = j0 < n; // n is a multiple of 16
+			uint4 pl[T];
+			uint32_t rst[T]; // offset (0..15) of a stream start inside the plane's 16 bytes, 16: none
+			uint32_t z[NP];
+#pragma unroll
+			for (int pp = 0; pp < NP; ++pp)
+				z[pp] = 0x01000100u; // identity maps
+#pragma unroll
+			for (int k = 0; k < T; ++k) {
+				pl[k] = make_uint4(0u, 0u, 0u, 0u);
+				rst[k] = 16u;
+				if (live) {
+					const uint64_t i0 = (uint64_t)k * n + j0;
+					pl[k] = *reinterpret_cast<const uint4*>(src + i0);
+					if (q1 - i0 < 16ull)
+						rst[k] = (uint32_t)(q1 - i0);
+					if (q2 - i0 < 16ull)
+						rst[k] = (uint32_t)(q2 - i0);
+					if (q3 - i0 < 16ull)
+						rst[k] = (uint32_t)(q3 - i0);
+					uint32_t m;
+					if (rst[k] == 16u)
+						m = 0x100u | ((sad4_acc(pl[k].x, 0u, 0u) + sad4_acc(pl[k].y, 0u, 0u) + sad4_acc(pl[k].z, 0u, 0u) + sad4_acc(pl[k].w, 0u, 0u)) & 0xFFu);
+					else {
+						uint32_t sum = 0; // bytes from the restart on
+						for (uint32_t b = rst[k]; b < 16u; ++b)
+							sum += byte16(pl[k], b);
+						m = sum & 0xFFu;
+					}
+					z[k >> 1] = (z[k >> 1] & ~(0x1FFu << (16 * (k & 1)))) | (m << (16 * (k & 1)));
+				}
+			}
+			// inclusive scan of the maps over the CTA: warp, then the warps' totals
+			uint32_t incl[NP];
+#pragma unroll
+			for (int pp = 0; pp < NP; ++pp) {
+				uint32_t x = z[pp];
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t y = __shfl_up_sync(FULL, x, d);
+					if (lane >= d)
+						x = compose_maps2(x, y);
+				}
+				incl[pp] = x;
+				if (lane == 31)
+					warp_maps[pp][warp] = x;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int pp = 0; pp < NP; ++pp) {
+				// maps of the warps before mine, composed; then everything before this thread
+				uint32_t w = lane < NW ? warp_maps[pp][lane] : 0x01000100u;
+#pragma unroll
+				for (int d = 1; d < NW; d <<= 1) {
+					const uint32_t y = __shfl_up_sync(FULL, w, d);
+					if (lane >= d)
+						w = compose_maps2(w, y);
+				}
+				const uint32_t tile_total = __shfl_sync(FULL, w, NW - 1);
+				uint32_t before_warp = __shfl_sync(FULL, w, (warp + NW - 1) % NW);
+				if (warp == 0)
+					before_warp = 0x01000100u;
+				uint32_t excl = __shfl_up_sync(FULL, incl[pp], 1); // threads before me in my warp
+				if (lane == 0)
+					excl = 0x01000100u;
+				// carry into this thread = (excl o before_warp)(run)
+				const uint32_t m = compose_maps2(excl, before_warp);
+				const uint32_t carry2 = compose_maps2(m, run[pp]) & 0x00FF00FFu;
+				run[pp] = compose_maps2(tile_total, run[pp]) & 0x00FF00FFu;
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const int k = 2 * pp + h;
+					const uint32_t carry = (carry2 >> (16 * h)) & 0xFFu;
+					uint32_t x[4] = { pl[k].x, pl[k].y, pl[k].z, pl[k].w }, o[4];
+					if (rst[k] == 16u)
+						prefix16(x, 0u, carry, o);
+					else {
+						// a stream starts inside the group: byte by byte
+						uint32_t acc = carry;
+						o[0] = o[1] = o[2] = o[3] = 0u;
+						for (uint32_t b = 0; b < 16u; ++b) {
+							if (b == rst[k])
+								acc = 0u;
+							acc = (acc + byte16(pl[k], b)) & 0xFFu;
+							o[b >> 2] |= acc << (8 * (b & 3));
+						}
+					}
+					pl[k] = make_uint4(o[0], o[1], o[2], o[3]);
+				}
+			}
+			__syncthreads();
+			if (live) {
+				uint32_t w[4 * T];
+				untranspose16<T>(pl, w);
+				uint4* d4 = reinterpret_cast<uint4*>(dst + j0 * T);
+#pragma unroll
+				for (int i = 0; i < T; ++i)
+					d4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+			}
+		}
+	}
 }

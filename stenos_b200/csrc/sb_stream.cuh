@@ -233,6 +233,8 @@ namespace sb
 			// sizes are final -> stream offset (look-back), ring position, room in the ring
 			uint32_t abs0 = 0, excl = 0;
 			auto place_pair = [&](uint32_t sz2) {
+				// (a serial chain -- wait for the predecessor's inclusive prefix only -- was measured at 1.45 ms against
+				// 0.75 ms: the links' store -> load round trips add up across the warps in flight)
 				if (lane == 0)
 					*reinterpret_cast<volatile uint32_t*>(&chain[j]) = (j == 0 ? CH_INC : CH_AGG) | sz2;
 				excl = chain_lookback(chain, j, lane);

@@ -133,7 +133,7 @@ def test_filters_match_oracle():
     for T in (2, 4, 8):
         for n in (0, 1, 100, 2048 // T + 1, 5000, 16384):
             a = rng.integers(0, 256, n * T + (int(rng.integers(0, T)) if n else 0), dtype=np.uint8)
-            for chunk in (0, 4096):
+            for chunk in (0, 4096, 2080 if T == 2 else 16 * T * 33):  # the last: fused unshuffle+delta_inv, T=2 with mid-group stream starts
                 step = chunk or max(a.size, 1)
                 pieces = [a[i:i + step] for i in range(0, a.size, step)]
                 sh = b"".join(port.shuffle(p, T) for p in pieces)

@@ -158,7 +158,7 @@ def test_filters_vs_oracle_with_chunks():
     ctx = api.Context()
     for wl, T in (("float64_sensor", 8), ("float32_sensor", 4), ("int16_sine", 2)):
         a = raw_of(synth.make(wl, (1 << 20) // T + 3))
-        for chunk in (131072, 262144, 524288):
+        for chunk in (131072, 262144, 524288, 2080 * T // 2, 16 * T * 1021):  # the last two: odd multiples of 16 elements (T=2: mid-group stream starts)
             pieces = [a[i:i + chunk] for i in range(0, a.size, chunk)]
             sh = b"".join(port.shuffle(p, T) for p in pieces)
             shd = b"".join(port.delta(np.frombuffer(port.shuffle(p, T), dtype=np.uint8)) for p in pieces)
