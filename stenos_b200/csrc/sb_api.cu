@@ -98,6 +98,26 @@ namespace
 		return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 	}
 
+	// Pinned (cudaHostAlloc / cudaHostRegister) host memory is addressable from kernels: returns its device alias, or
+	// nullptr for pageable host memory and device pointers.
+	uint8_t* pinned_alias(const void* p)
+	{
+		if (!p)
+			return nullptr;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+		return a.type == cudaMemoryTypeHost ? static_cast<uint8_t*>(a.devicePointer) : nullptr;
+	}
+	// experiments: STENOS_B200_ZERO_COPY bit 0: kernels read pinned host input in place, bit 1: write pinned host output in place
+	int zero_copy_mode()
+	{
+		const char* e = getenv("STENOS_B200_ZERO_COPY");
+		return e ? atoi(e) : 0;
+	}
+
 	// super_block_size(), stenos.cpp:71-76
 	size_t default_superblock(size_t T)
 	{
@@ -130,6 +150,30 @@ struct stenos_context_s
 	bool env_read = false;
 	bool index_ran = false;    // a parallel frame index was enqueued (its verdict is in scan.p)
 	unsigned long long* host_result = nullptr; // pinned, 4 words
+	// host <-> device pipeline of stenos_compress_generic on host buffers: copy streams, per-chunk events and results
+	static constexpr int PIPE_MAX = 64;
+	cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
+	cudaEvent_t pipe_ev[2 * PIPE_MAX] = {};
+	unsigned long long* pipe_host = nullptr; // pinned, 2 words per chunk
+	DevBuf pipe_res;                         // 2 words per chunk
+	bool pipe_ready = false;
+	bool pipe_init()
+	{
+		if (pipe_ready)
+			return true;
+		if (cudaStreamCreateWithFlags(&pipe_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&pipe_out, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaMallocHost((void**)&pipe_host, PIPE_MAX * 16) != cudaSuccess || !pipe_res.reserve(PIPE_MAX * 16)) {
+			cudaGetLastError();
+			return false;
+		}
+		for (int i = 0; i < 2 * PIPE_MAX; ++i)
+			if (cudaEventCreateWithFlags(&pipe_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+				cudaGetLastError();
+				return false;
+			}
+		pipe_ready = true;
+		return true;
+	}
 	int sm_count = 0;
 
 	cudaStream_t stream()
@@ -212,6 +256,21 @@ struct stenos_context_s
 		if (host_result)
 			cudaFreeHost(host_result);
 		host_result = nullptr;
+		if (pipe_host)
+			cudaFreeHost(pipe_host);
+		pipe_host = nullptr;
+		for (int i = 0; i < 2 * PIPE_MAX; ++i)
+			if (pipe_ev[i]) {
+				cudaEventDestroy(pipe_ev[i]);
+				pipe_ev[i] = nullptr;
+			}
+		if (pipe_in)
+			cudaStreamDestroy(pipe_in);
+		if (pipe_out)
+			cudaStreamDestroy(pipe_out);
+		pipe_in = pipe_out = nullptr;
+		pipe_res.release();
+		pipe_ready = false;
 		if (own_stream_made && own_stream)
 			cudaStreamDestroy(own_stream);
 		own_stream = nullptr;
@@ -544,6 +603,37 @@ namespace
 		return true;
 	}
 
+	// The final superblock of a level-1 frame when it is shorter than 128 bytes (stenos.cpp:435-437, :658-674): Zstd level 1
+	// through the host's libzstd, stored raw if that does not shrink it.  tail, out: host memory; room: bytes left in dst.
+	// Returns the bytes written ([code][len:3][payload]) or an error code.
+	size_t encode_host_tail(const uint8_t* tail, size_t last_bytes, uint8_t* out, size_t room)
+	{
+		uint8_t enc[4 + 256];
+		if (room < 4)
+			return STENOS_ERROR_DST_OVERFLOW;
+		if (!load_zstd())
+			return STENOS_ERROR_ZSTD_INTERNAL;
+		size_t len = 0;
+		// zstd_compress_with_context(dst + 4, dst_size - 4, src, bytes, 0) -> zstd level 1 (zstd_wrapper.h:49-56)
+		const size_t zr = p_zstd_compress(enc + 4, std::min<size_t>(room - 4, 256), tail, last_bytes, 1);
+		if (!p_zstd_iserror(zr) && zr <= last_bytes) {
+			len = zr;
+			enc[0] = (uint8_t)CODE_ZSTD;
+		}
+		else { // stenos.cpp:668-669 -> MEMCPY
+			if (room < last_bytes + 4)
+				return STENOS_ERROR_DST_OVERFLOW;
+			enc[0] = (uint8_t)CODE_COPY;
+			memcpy(enc + 4, tail, last_bytes);
+			len = last_bytes;
+		}
+		enc[1] = (uint8_t)len;
+		enc[2] = (uint8_t)(len >> 8);
+		enc[3] = (uint8_t)(len >> 16);
+		memcpy(out, enc, len + 4);
+		return len + 4;
+	}
+
 	// Common body of stenos_compress_generic and stenos_private_compress_block.
 	// frame = true : [frame header] + superblocks;   frame = false: one bare superblock
 	size_t compress_impl(stenos_context* ctx, const void* src_, size_t T, size_t bytes, void* dst_, size_t dst_size, bool frame, size_t sb)
@@ -589,10 +679,90 @@ namespace
 		const bool host_tail = level >= 1 && n_sb && last_bytes < 128 && bytes != 0;
 		const size_t dev_bytes = host_tail ? bytes - last_bytes : bytes;
 
+		// ---- host -> host through the device, pipelined: the input travels in chunks of whole superblocks; chunk i is
+		// encoded (as an independent segment, into its own worst-case region) while chunk i + 1 is still on the bus, and
+		// its stream leaves for the caller's buffer while later chunks are encoded.  Taken only when the caller's dst
+		// leaves every superblock ample room (then the reference's room checks are inert, SURVEY.md appendix C2, and
+		// the concatenated segments ARE the frame); otherwise the single launch below keeps the exact room arithmetic.
+		// (STENOS_B200_PIPELINE_CHUNK = chunk bytes, tests: small frames take the path too; 0 = off)
+		const char* pipe_env = getenv("STENOS_B200_PIPELINE_CHUNK");
+		const size_t pipe_chunk = pipe_env ? (size_t)strtoull(pipe_env, nullptr, 10) : ((size_t)32 << 20);
+		if (frame && !src_dev && !dst_dev && level >= 1 && pipe_chunk && dev_bytes >= 2 * pipe_chunk) {
+			const uint64_t block = T * 256, hs = (T + 1) / 2;
+			const uint64_t need = (sb / block) * (block + hs) + 8 * T + 32 + 8 * T + block;
+			const size_t dev_sb = (dev_bytes + sb - 1) / sb;
+			if (dst_size >= (uint64_t)header_len + 4 + need + (uint64_t)(dev_sb - 1) * (4 + sb) && ctx->pipe_init()) {
+				size_t chunk = std::max<size_t>(pipe_chunk, (dev_bytes + stenos_context_s::PIPE_MAX - 1) / stenos_context_s::PIPE_MAX);
+				chunk = (chunk + sb - 1) / sb * sb;
+				const size_t n_chunk = (dev_bytes + chunk - 1) / chunk;
+				const size_t region = 16 + (chunk / sb) * (4 + sb) + need + 64; // worst case of a chunk + the slack that keeps all of it on the fast path
+				if (n_chunk >= 2 && n_chunk <= (size_t)stenos_context_s::PIPE_MAX && ctx->in.reserve(dev_bytes + 16) && ctx->out.reserve(n_chunk * region + 16)) {
+					unsigned long long* d_res = reinterpret_cast<unsigned long long*>(ctx->pipe_res.p);
+					cudaEventRecord(ctx->pipe_ev[0], st); // work already queued on the context's stream comes first
+					cudaStreamWaitEvent(ctx->pipe_in, ctx->pipe_ev[0], 0);
+					for (size_t i = 0; i < n_chunk; ++i) {
+						const size_t off = i * chunk, len = std::min(chunk, dev_bytes - off);
+						cudaMemcpyAsync(ctx->in.p + off, src + off, len, cudaMemcpyHostToDevice, ctx->pipe_in);
+						cudaEventRecord(ctx->pipe_ev[2 * i + 1], ctx->pipe_in);
+					}
+					size_t err = 0;
+					for (size_t i = 0; i < n_chunk && !err; ++i) {
+						const size_t off = i * chunk, len = std::min(chunk, dev_bytes - off);
+						cudaStreamWaitEvent(st, ctx->pipe_ev[2 * i + 1], 0);
+						const size_t r = enqueue_encode(ctx, ctx->in.p + off, T, len, ctx->out.p + i * region, region, sb, i == 0 ? header_len : 0u, (uint32_t)ctx->shift, bytes, level,
+										d_res + 2 * i, nullptr);
+						if (is_err(r))
+							err = r;
+						cudaMemcpyAsync(ctx->pipe_host + 2 * i, d_res + 2 * i, 16, cudaMemcpyDeviceToHost, st);
+						cudaEventRecord(ctx->pipe_ev[2 * i], st);
+					}
+					size_t total = 0;
+					for (size_t i = 0; i < n_chunk && !err; ++i) {
+						if (cudaEventSynchronize(ctx->pipe_ev[2 * i]) != cudaSuccess) {
+							cudaGetLastError();
+							err = STENOS_ERROR_UNDEFINED;
+							break;
+						}
+						err = map_device_error(ctx->pipe_host[2 * i + 1]);
+						const size_t len = (size_t)ctx->pipe_host[2 * i];
+						if (!err && total + len > dst_size)
+							err = STENOS_ERROR_DST_OVERFLOW;
+						if (err)
+							break;
+						cudaMemcpyAsync(dst + total, ctx->out.p + i * region, len, cudaMemcpyDeviceToHost, ctx->pipe_out);
+						total += len;
+					}
+					cudaStreamSynchronize(ctx->pipe_in);
+					cudaStreamSynchronize(st);
+					if (cudaStreamSynchronize(ctx->pipe_out) != cudaSuccess) {
+						cudaGetLastError();
+						return STENOS_ERROR_UNDEFINED;
+					}
+					if (err)
+						return err;
+					if (host_tail) {
+						const size_t tr = encode_host_tail(src + dev_bytes, last_bytes, dst + total, dst_size - total);
+						if (is_err(tr))
+							return tr;
+						total += tr;
+					}
+					return total;
+				}
+			}
+		}
+
 		// ---- stage input
 		const uint8_t* d_src = src;
+		const int zc = (src_dev && dst_dev) ? 0 : zero_copy_mode();
+		bool src_direct = src_dev;
+		if (!src_dev && (zc & 1)) {
+			if (const uint8_t* a = pinned_alias(src)) {
+				d_src = a;
+				src_direct = true;
+			}
+		}
 		if (dev_bytes) {
-			if (!src_dev || ((uintptr_t)src & 15u)) {
+			if (!src_direct || ((uintptr_t)d_src & 15u)) {
 				if (!ctx->in.reserve(dev_bytes + 16))
 					return STENOS_ERROR_ALLOC;
 				cudaMemcpyAsync(ctx->in.p, src, dev_bytes, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
@@ -602,7 +772,14 @@ namespace
 		// ---- output
 		uint8_t* d_dst = dst;
 		size_t d_cap = dst_size;
-		if (!dst_dev) {
+		bool dst_direct = dst_dev;
+		if (!dst_dev && (zc & 2)) {
+			if (uint8_t* a = pinned_alias(dst)) {
+				d_dst = a;
+				dst_direct = true;
+			}
+		}
+		if (!dst_direct) {
 			// The staging buffer never needs more than the worst case of the frame (every superblock
 			// stored as COPY); the kernel still receives the caller's dst_size because the reference's
 			// room arithmetic depends on it.
@@ -618,7 +795,7 @@ namespace
 			if (bytes == 0) {
 				// empty bare superblock: [6][0:3] (stenos.cpp:431-433)
 				const uint8_t h[4] = { (uint8_t)CODE_COPY, 0, 0, 0 };
-				cudaMemcpyAsync(d_dst, h, 4, cudaMemcpyHostToDevice, st);
+				cudaMemcpyAsync(d_dst, h, 4, cudaMemcpyDefault, st);
 				cudaStreamSynchronize(st);
 				total = 4;
 				r = 0;
@@ -642,7 +819,7 @@ namespace
 			// only a tiny tail: the header is written from the host
 			uint8_t h[12];
 			write_frame_header(h, ctx->shift, bytes, sb, custom);
-			cudaMemcpyAsync(d_dst, h, header_len, cudaMemcpyHostToDevice, st);
+			cudaMemcpyAsync(d_dst, h, header_len, cudaMemcpyDefault, st);
 		}
 
 		if (host_tail) {
@@ -677,11 +854,11 @@ namespace
 			enc[1] = (uint8_t)len;
 			enc[2] = (uint8_t)(len >> 8);
 			enc[3] = (uint8_t)(len >> 16);
-			cudaMemcpyAsync(d_dst + total, enc, len + 4, cudaMemcpyHostToDevice, st);
+			cudaMemcpyAsync(d_dst + total, enc, len + 4, cudaMemcpyDefault, st);
 			cudaStreamSynchronize(st);
 			total += len + 4;
 		}
-		if (!dst_dev) {
+		if (!dst_direct) {
 			cudaMemcpyAsync(dst, d_dst, total, cudaMemcpyDeviceToHost, st);
 			if (cudaStreamSynchronize(st) != cudaSuccess) {
 				cudaGetLastError();

@@ -634,6 +634,18 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned)
 	return cudaSuccess;
 }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+// events: everything in the emulator runs synchronously, so they are always complete
+typedef void* cudaEvent_t;
+#define cudaEventDisableTiming 2
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned)
+{
+	*e = reinterpret_cast<cudaEvent_t>(1);
+	return cudaSuccess;
+}
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d)
 {

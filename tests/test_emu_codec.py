@@ -225,3 +225,19 @@ def test_row_decoder_every_distribution(T):
         assert api.Context().decompress(c, T, raw.size) == raw.tobytes()
     finally:
         del os.environ["STENOS_B200_LEGACY_DECODER"]
+
+
+def test_pipelined_host_path_matches_single_launch(monkeypatch):
+    """stenos_compress_generic on host buffers: chunks of whole superblocks encoded as segments while later chunks
+    are still being copied in; the concatenation must be the frame (incl. the < 128 byte Zstd tail)."""
+    for T, n in ((4, (5 * 131072 + 4 * 256 * 3 + 100) // 4), (2, (4 * 131072 + 60) // 2), (8, (3 * 131072 + 8 * 300) // 8)):
+        rng = np.random.default_rng(11)
+        a = (np.arange(n) * 3 + rng.integers(0, 16, n)).astype({2: np.int16, 4: np.int32, 8: np.int64}[T])
+        raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        want = port.compress(raw, T)
+        monkeypatch.setenv("STENOS_B200_PIPELINE_CHUNK", str(131072))
+        got = run(api.compress, raw, T)
+        monkeypatch.setenv("STENOS_B200_PIPELINE_CHUNK", "0")
+        single = run(api.compress, raw, T)
+        assert got == want and single == want
+        assert run(api.decompress, got, T, raw.size) == raw.tobytes()

@@ -309,11 +309,24 @@ def test_stream_encoder_mixed_superblocks(T, n_sb, tail):
     room = raw.size + 300000
     want = port.compress(raw, T, dst_size=room)
     ctx = api.Context()
-    l0 = api.kernel_launches()
-    got = ctx.compress(raw, T, dst_size=room)
-    assert api.kernel_launches() - l0 == 1
+    os.environ["STENOS_B200_PIPELINE_CHUNK"] = "0"  # one launch for the whole frame
+    try:
+        l0 = api.kernel_launches()
+        got = ctx.compress(raw, T, dst_size=room)
+        assert api.kernel_launches() - l0 == 1
+    finally:
+        del os.environ["STENOS_B200_PIPELINE_CHUNK"]
     assert got == want
     assert ctx.decompress(got, T, raw.size) == raw.tobytes()
+    # host buffers, pipelined: chunks of whole superblocks as independent segments, copies overlapped with the kernels
+    os.environ["STENOS_B200_PIPELINE_CHUNK"] = str(8 << 20)
+    try:
+        l0 = api.kernel_launches()
+        assert ctx.compress(raw, T, dst_size=room) == want
+        n_launch = api.kernel_launches() - l0
+        assert n_launch >= 2 if raw.size >= (16 << 20) else n_launch == 1
+    finally:
+        del os.environ["STENOS_B200_PIPELINE_CHUNK"]
     os.environ["STENOS_B200_LEGACY_ENCODER"] = "1"
     try:
         assert api.Context().compress(raw, T, dst_size=room) == want
