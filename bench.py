@@ -194,7 +194,10 @@ def main():
     ctx = api.Context(level=1, stream=stream)
     seg = distributed.SegmentCodec(ctx, T, frame_bytes)
     d_src = host.to(dev)
-    cap = seg.capacity(nbytes) + 16
+    # device-resident destination: the worst case of the frame plus 1 MiB, so that every superblock -- the last one too --
+    # provably has the room in which the reference's dst-room checks are inert and the whole
+    # frame is one launch of the stream encoder; the e2e leg below uses stenos_bound(bytes) exactly
+    cap = seg.capacity(nbytes) + (1 << 20)
     d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
     d_res = torch.zeros(2, dtype=torch.int64, device=dev)
     n_sb = (nbytes + seg.sb - 1) // seg.sb
@@ -300,7 +303,7 @@ def main():
         "ms_per_step": c_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "%d GiB int32 noisy ramp + runs per GPU (BASELINE.json configs[1]), level 1, one frame of %d GiB" % (nbytes >> 30, frame_bytes >> 30)
                    if nbytes >= (1 << 30) else "%d MiB int32 noisy ramp + runs per GPU, level 1" % (nbytes >> 20),
-                   "bytesoftype": T, "superblock": seg.sb, "l2": "inputs larger than L2 (no flush needed)",
+                   "bytesoftype": T, "superblock": seg.sb, "l2": "inputs larger than L2 (no flush needed)", "device_dst_capacity": "stenos_bound(bytes) + 1 MiB",
                    "parallelism": "superblock ranges per GPU, segment sizes all-gathered" if world > 1 else "1 GPU"},
         "decompress_GBps": frame_bytes / (d_step_ms * 1e-3) / 1e9, "decompress_ms_per_step": d_step_ms,
         "ratio": nbytes / csize, "compressed_bytes_per_gpu": csize,

@@ -503,6 +503,8 @@ namespace
 		// segments of about half a superblock: every warp re-synchronises within one superblock and walks a few
 		// hops; at most 65536 segments so the single-CTA merge stays short
 		size_t seg = std::min<size_t>(std::max<size_t>(sb / 2, 4096), 65536);
+		if (const char* e = getenv("STENOS_B200_INDEX_SEG")) // experiments
+			seg = std::max<size_t>((size_t)strtoull(e, nullptr, 10), 4096);
 		const size_t span = size > first ? size - first : 0;
 		if ((span + seg - 1) / seg > 65536)
 			seg = (span + 65535) / 65536;
