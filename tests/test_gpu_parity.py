@@ -342,3 +342,23 @@ def test_stream_encoder_many_tiny_superblocks():
     want = port.compress(raw, 4, block_shift=0, dst_size=room)
     assert ctx.compress(raw, 4, dst_size=room) == want
     assert api.decompress(want, 4, raw.size) == raw.tobytes()
+
+
+def test_unchanged_cvector_header_is_a_drop_in(tmp_path):
+    """the reference's unchanged stenos/cvector.hpp compiled against libstenos_b200.so (oracle/Makefile,
+    target cvector; tests/cpp/cvector_dropin.cpp) behaves like the same program linked against the reference: same
+    element values after push_back / random writes / iteration, and the same serialized bytes (the cvector room rule
+    T*256+16 per bucket)."""
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "cvector_dropin_ref")
+    b200_bin = os.path.join(ROOT, "oracle", "_ref", "cvector_dropin_b200")
+    if not (os.path.exists(ref_bin) and os.path.exists(b200_bin)):
+        pytest.skip("drop-in binaries not built (make -C oracle cvector needs /root/reference)")
+    a, b = str(tmp_path / "ref.bin"), str(tmp_path / "b200.bin")
+    ra = subprocess.run([ref_bin, a], capture_output=True, text=True, timeout=300)
+    rb = subprocess.run([b200_bin, b], capture_output=True, text=True, timeout=600)
+    assert ra.returncode == 0, ra.stdout + ra.stderr
+    assert rb.returncode == 0, rb.stdout + rb.stderr
+    assert ra.stdout == rb.stdout
+    assert open(a, "rb").read() == open(b, "rb").read()
