@@ -68,6 +68,8 @@ def test_plan_partition():
 
 
 def test_two_rank_gloo_partition():
+    # build the emulator library once, here: two ranks running `make` on the same target at the same time race
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -76,7 +78,7 @@ def test_two_rank_gloo_partition():
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, "-c", WORKER % {"root": ROOT}], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
