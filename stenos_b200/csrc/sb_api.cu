@@ -386,7 +386,8 @@ namespace
 			{
 				// experiment knob: fewer resident CTAs per SM than the occupancy allows
 				static const int cap = [] { const char* e = getenv("STENOS_B200_DECODE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-				static const int split_off = [] { const char* e = getenv("STENOS_B200_SPLIT_DECODER"); return e && e[0] == '1' ? 0 : 1; }(); // experimental: sb_decode_split.cuh
+				const char* split_env = getenv("STENOS_B200_SPLIT_DECODER"); // experimental: sb_decode_split.cuh
+				const int split_off = split_env && split_env[0] == '1' ? 0 : 1;
 				if (!split_off) {
 					// parser threads walk the block streams, half-warps decode single blocks behind them (sb_decode_split.cuh)
 					const uint32_t block = (uint32_t)T * 256u;

@@ -362,3 +362,21 @@ def test_unchanged_cvector_header_is_a_drop_in(tmp_path):
     assert rb.returncode == 0, rb.stdout + rb.stderr
     assert ra.stdout == rb.stdout
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_split_decoder_matches(monkeypatch):
+    """The opt-in parser/decoder split kernel (STENOS_B200_SPLIT_DECODER=1, sb_decode_split.cuh) against the oracle's
+    streams: mixed superblocks of every kind, partial tails, corrupt input."""
+    monkeypatch.setenv("STENOS_B200_SPLIT_DECODER", "1")
+    rng = np.random.default_rng(22)
+    for T in (2, 4, 8):
+        raw = _mixed(T, 40, seed=90 + T, tail_elems=100)
+        c = port.compress(raw, T)
+        assert api.decompress(c, T, raw.size) == raw.tobytes()
+        bad = bytearray(c)
+        for i in rng.integers(12, len(bad), 60):
+            bad[i] ^= 0xA5
+        try:
+            api.decompress(bytes(bad), T, raw.size)
+        except (api.StenosError, RuntimeError):
+            pass
