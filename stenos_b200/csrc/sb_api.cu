@@ -300,7 +300,7 @@ namespace
 #define STREAM_THREADS_4 640
 #endif
 #ifndef STREAM_THREADS_8
-#define STREAM_THREADS_8 256
+#define STREAM_THREADS_8 384
 #endif
 
 	// ---- launchers ------------------------------------------------------------------------------

@@ -19,7 +19,10 @@
 	extern __shared__ __align__(16) uint8_t stenos_dyn_smem_raw[]; \
 	type* name = reinterpret_cast<type*>(stenos_dyn_smem_raw)
 #define STENOS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#define STENOS_SPIN_HINT() __nanosleep(20)
+#ifndef STENOS_SPIN_HINT_NS
+#define STENOS_SPIN_HINT_NS 20
+#endif
+#define STENOS_SPIN_HINT() __nanosleep(STENOS_SPIN_HINT_NS)
 #define STENOS_SPIN_WAIT() __nanosleep(200) // waits that are expected to be long
 #endif
 

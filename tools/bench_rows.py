@@ -23,6 +23,8 @@ import torch
 from stenos_b200 import api, capi, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if os.environ.get("STENOS_B200_LIB"):  # experiment builds (tools/build_variant.py)
+    capi.use_library(capi.load(os.environ["STENOS_B200_LIB"]))
 
 
 def peak():

@@ -18,9 +18,9 @@ def timeit(fn, n=5, w=2):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
-    T = 4
+    T = int(os.environ.get("TP_T", "4"))
     dev = torch.device("cuda:0")
-    a = synth.make("int32_ramp_runs", n)
+    a = synth.make({2: "int16_sine", 4: "int32_ramp_runs", 8: "int64_ramp_runs"}[T], n * 4 // T)
     d_src = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
     nbytes = d_src.numel()
     ctx = api.Context(level=1, stream=torch.cuda.current_stream())
