@@ -718,6 +718,12 @@ namespace sb
 #ifndef DECODE2_WARPS_PER_CTA
 #define DECODE2_WARPS_PER_CTA 4
 #endif
+#ifndef DECODE2_MIN_CTAS_T2
+#define DECODE2_MIN_CTAS_T2 7 // 72 registers without spills: 28 warps per SM (1.28 -> 0.95 ms per GiB of int16)
+#endif
+#ifndef DECODE2_MIN_CTAS_T8
+#define DECODE2_MIN_CTAS_T8 7 // spills, but 56 streams per SM hold 1 GiB in one round (0.66 -> 0.61 ms); T=4 gains nothing
+#endif
 #ifndef DECODE2_MIN_CTAS
 #define DECODE2_MIN_CTAS 6
 #endif
@@ -726,7 +732,7 @@ namespace sb
 	// frame decoder: persistent warps; a warp takes the next two superblocks (one per half-warp) by ticket, so
 	// streams of very different cost (constant data next to noisy data) do not leave SMs idle behind a slow CTA
 	template<int T>
-	__global__ void __launch_bounds__(DECODE2_WARPS * 32, DECODE2_MIN_CTAS) decode_pairs_kernel(DecodeParams P)
+	__global__ void __launch_bounds__(DECODE2_WARPS * 32, (T == 2 ? DECODE2_MIN_CTAS_T2 : T == 8 ? DECODE2_MIN_CTAS_T8 : DECODE2_MIN_CTAS)) decode_pairs_kernel(DecodeParams P)
 	{
 		STENOS_DYN_SMEM(uint8_t, smem);
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
