@@ -152,7 +152,7 @@ def run_reference(args, rank):
                          "sample": "%d MiB of %s, stenos_set_threads=%d, AVX2 build of /root/reference" % (m["bytes"] >> 20, WORKLOAD, cores)},
         "e2e": {"value": m["compress_GBps"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -173,6 +173,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there meanwhile (NCCL's version banner at the
+    # first collective) is sent to stderr, and the real stdout comes back for the last print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -332,7 +338,9 @@ def main():
             t0 = time.perf_counter()
             port.compress(s, T)
             line["cpu_baseline"] = {"value": s.size / (time.perf_counter() - t0) / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "sample": "16 MiB, scalar C port"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
