@@ -469,8 +469,8 @@ namespace sb
 				const uint64_t xb = x0 + 16ull * lane;
 				unsigned long long found = IDX_NONE;
 				uint32_t cand = 0;
+				uint32_t w[5] = { 0u, 0u, 0u, 0u, 0u };
 				if (xb < scan_end) {
-					uint32_t w[4];
 					const uint8_t* p = P.src + xb;
 					if (xb + 16 <= P.src_size && (((uintptr_t)p) & 3u) == 0) {
 #pragma unroll
@@ -487,9 +487,23 @@ namespace sb
 							w[j] = v;
 						}
 					}
+				}
+				// A header's csize is at most max_csize, so its top byte (3 bytes after the code) is small: a second SWAR
+				// filter on the bytes already loaded (the next lane holds the 3 bytes past mine) removes nearly all of the
+				// code-byte look-alikes before the chain check, which costs dependent loads.
+				w[4] = __shfl_down_sync(FULL, w[0], 1);
+				if (lane == 31)
+					w[4] = 0u; // unknown: lets the last three positions pass
+				if (xb < scan_end) {
+					const uint32_t hi_max = P.max_csize >> 16;
+					const uint32_t kadd = hi_max < 0x7Fu ? (0x7Fu - hi_max) * 0x01010101u : 0u;
 #pragma unroll
 					for (int j = 0; j < 4; ++j) {
-						const uint32_t z = zero_bytes(w[j] ^ 0x01010101u) | zero_bytes(w[j] ^ 0x06060606u) | zero_bytes(w[j] ^ 0x02020202u);
+						uint32_t z = zero_bytes(w[j] ^ 0x01010101u) | zero_bytes(w[j] ^ 0x06060606u) | zero_bytes(w[j] ^ 0x02020202u);
+						if (hi_max < 0x7Fu) {
+							const uint32_t t3 = __funnelshift_r(w[j], w[j + 1], 24); // byte b + 3 at position b
+							z &= ~(((t3 & 0x7F7F7F7Fu) + kadd) | t3);
+						}
 						cand |= flags_to_mask4(z) << (4 * j);
 					}
 				}
