@@ -464,9 +464,18 @@ namespace
 			STENOS_LAUNCH(gather_decode_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
 		}
 		else {
+			// persistent warps, bucket pairs round robin (the kernel pipelines its random accesses across iterations)
 			const unsigned warps = (P.n + 1) / 2;
-			const unsigned grid = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
-			STENOS_LAUNCH(gather_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * 512, ctx->stream(), P);
+			const unsigned need = (warps + DECODE2_WARPS - 1) / DECODE2_WARPS;
+			int per_sm = 1;
+#ifndef STENOS_EMU
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_pairs_kernel<T>, DECODE2_WARPS * 32, DECODE2_WARPS * (512 + 128)) != cudaSuccess || per_sm < 1) {
+				cudaGetLastError();
+				per_sm = 1;
+			}
+#endif
+			const unsigned grid = std::min<unsigned>(need, (unsigned)(ctx->sm_count * per_sm));
+			STENOS_LAUNCH(gather_pairs_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), DECODE2_WARPS * (512 + 128), ctx->stream(), P);
 		}
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;

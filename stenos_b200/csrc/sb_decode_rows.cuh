@@ -758,29 +758,74 @@ namespace sb
 		}
 	}
 
-	// stenos::cvector random access: one half-warp per requested bucket (cvector.hpp:2879 -> :1862-1883)
+	// stenos::cvector random access: one half-warp per requested bucket (cvector.hpp:2879 -> :1862-1883).
+	// A bucket is three dependent random accesses away (its id, its offset, its bytes), so persistent warps run a
+	// four stage software pipeline over their bucket pairs -- id of pair n + 3, offset of pair n + 2, the lines of
+	// pair n + 1 on their way to L1, pair n decoded -- and no stage waits for the latency of the one before.
+#ifndef GATHER_MIN_CTAS
+#define GATHER_MIN_CTAS 5 // 96 registers, no spills: measured best of 3..7
+#endif
 	template<int T>
-	__global__ void __launch_bounds__(DECODE2_WARPS * 32) gather_pairs_kernel(GatherParams P)
+	__global__ void __launch_bounds__(DECODE2_WARPS * 32, GATHER_MIN_CTAS) gather_pairs_kernel(GatherParams P)
 	{
 		STENOS_DYN_SMEM(uint8_t, smem);
-		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, r = lane & 15;
 		uint16_t* lz_scratch = reinterpret_cast<uint16_t*>(smem) + 256 * warp;
-		const uint32_t i = 2u * (blockIdx.x * DECODE2_WARPS + warp) + (uint32_t)(lane >> 4);
-		if (i - (uint32_t)(lane >> 4) >= P.n)
-			return;
-		bool valid = i < P.n;
-		const uint32_t id = valid ? P.ids[i] : 0u;
-		uint32_t bad = 0;
-		if (valid && id >= P.n_buckets) {
-			bad = DEV_ERR_INVALID_INPUT;
-			valid = false;
+		void* scratch_word = smem + DECODE2_WARPS * 512 + 4 * threadIdx.x;
+		const uint32_t n_warps = gridDim.x * DECODE2_WARPS;
+		const uint32_t w0 = blockIdx.x * DECODE2_WARPS + warp;
+		const uint32_t n_pairs = (P.n + 1u) / 2u;
+		const uint8_t* lim = P.src + P.src_size;
+		// pipeline registers of this half: request index (>= P.n: nothing), bucket id, offset of its header
+		uint32_t i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu, i3 = 0xFFFFFFFFu, id1 = 0, id2 = 0, id3 = 0;
+		unsigned long long off1 = 0, off2 = 0;
+		auto fetch_id = [&](uint32_t pair, uint32_t& i, uint32_t& id) {
+			i = pair < n_pairs ? 2u * pair + (uint32_t)half : 0xFFFFFFFFu;
+			if (i >= P.n)
+				i = 0xFFFFFFFFu;
+			id = i != 0xFFFFFFFFu ? P.ids[i] : 0u;
+		};
+		auto fetch_off = [&](uint32_t i, uint32_t id) -> unsigned long long { return (i != 0xFFFFFFFFu && id < P.n_buckets) ? P.sb_offsets[id] : 0ull; };
+		auto touch = [&](uint32_t i, uint32_t id, unsigned long long off) {
+			if (i != 0xFFFFFFFFu && id < P.n_buckets && r < 2) {
+				// a bucket of one block: its header and the first lines of its stream (the rest is asked for on demand)
+				const uint8_t* a = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(P.src + off) & ~(uintptr_t)127) + 128u * (uint32_t)r);
+				if (a >= P.src && a + 128 <= lim)
+					prefetch_l1_async(a, scratch_word);
+			}
+		};
+		fetch_id(w0, i1, id1);
+		fetch_id(w0 + n_warps, i2, id2);
+		fetch_id(w0 + 2u * n_warps, i3, id3);
+		off1 = fetch_off(i1, id1);
+		off2 = fetch_off(i2, id2);
+		touch(i1, id1, off1);
+		for (uint32_t pair = w0; pair < n_pairs; pair += n_warps) {
+			const uint32_t i = i1, id = id1;
+			const unsigned long long off = off1;
+			// advance the pipeline: the loads issued here are consumed one iteration later
+			i1 = i2;
+			id1 = id2;
+			off1 = off2;
+			i2 = i3;
+			id2 = id3;
+			touch(i1, id1, off1);
+			off2 = fetch_off(i2, id2);
+			fetch_id(pair + 3u * n_warps, i3, id3);
+
+			bool valid = i != 0xFFFFFFFFu;
+			uint32_t bad = 0;
+			if (valid && id >= P.n_buckets) {
+				bad = DEV_ERR_INVALID_INPUT;
+				valid = false;
+			}
+			const uint64_t doff = (uint64_t)id * P.bucket_bytes;
+			const uint32_t dsize = valid ? (uint32_t)min((uint64_t)P.bucket_bytes, P.total - doff) : 0u;
+			const uint32_t e = decode_superblock_pair<T>(P.src, P.src_size, valid ? off : 0ull, dsize, P.dst + (uint64_t)(valid ? i : 0u) * P.bucket_bytes, valid, false, lz_scratch,
+								     lane, scratch_word);
+			bad |= e;
+			if (bad && (lane & 15) == 0)
+				atomicOr(&P.result[1], (unsigned long long)bad);
 		}
-		const uint64_t doff = (uint64_t)id * P.bucket_bytes;
-		const uint32_t dsize = valid ? (uint32_t)min((uint64_t)P.bucket_bytes, P.total - doff) : 0u;
-		const uint32_t e = decode_superblock_pair<T>(P.src, P.src_size, valid ? P.sb_offsets[id] : 0ull, dsize, P.dst + (uint64_t)i * P.bucket_bytes, valid, false, lz_scratch,
-							     lane);
-		bad |= e;
-		if (bad && (lane & 15) == 0)
-			atomicOr(&P.result[1], (unsigned long long)bad);
 	}
 }
