@@ -382,7 +382,10 @@ namespace sb
 	// is an affine map last = a * prev + c with a = 0 if it holds a restart, and the CTA scans maps, two planes per
 	// register (compose_maps2).  Requires cb % (16 * T) == 0 and 16-byte aligned chunks (the host checks).
 	// ------------------------------------------------------------------------------------------
-	constexpr int UNSHUFFLE_DELTA_THREADS = 512;
+#ifndef UNSHUFFLE_DELTA_NT
+#define UNSHUFFLE_DELTA_NT 128 // measured: 128 > 256 > 512 > 1024 threads (more CTAs per SM, cheaper barriers)
+#endif
+	constexpr int UNSHUFFLE_DELTA_THREADS = UNSHUFFLE_DELTA_NT;
 	template<int T>
 	__global__ void __launch_bounds__(UNSHUFFLE_DELTA_THREADS) unshuffle_delta_kernel(FilterParams P)
 	{
@@ -433,6 +436,15 @@ namespace sb
 		for (uint64_t t0 = 0; t0 < n; t0 += (uint64_t)UNSHUFFLE_DELTA_THREADS * 16) {
 			const uint64_t j0 = t0 + (uint64_t)tid * 16;
 			const bool live = j0 < n; // n is a multiple of 16
+			// the next tile's lines start their way to L2 now (one request per 128-byte line)
+			if ((tid & 7) == 0) {
+				const uint64_t jn = j0 + (uint64_t)UNSHUFFLE_DELTA_THREADS * 16;
+				if (jn < n) {
+#pragma unroll
+					for (int k = 0; k < T; ++k)
+						prefetch_l2(src + (uint64_t)k * n + jn);
+				}
+			}
 			uint4 pl[T];
 			uint32_t rst[T]; // offset (0..15) of a stream start inside the plane's 16 bytes, 16: none
 			uint32_t z[NP];

@@ -75,12 +75,12 @@ def row_codec(T, name, nbytes, dev, pk):
 
 
 def row_filters(T, name, nbytes, chunk, dev, pk):
-    lib = capi.load()
     a = synth.make(name, nbytes // T)
     d_src = to_dev(a, dev)
     d_a = torch.empty_like(d_src)
     d_b = torch.empty_like(d_src)
     ctx = api.Context(level=1, stream=torch.cuda.current_stream())
+    lib = ctx._lib  # the library the context was made by (STENOS_B200_LIB experiments included)
     out = {"row": "filters", "T": T, "data": name, "bytes": nbytes, "chunk": chunk}
     for wd in (0, 1):
         tag = "+delta" if wd else ""
