@@ -120,6 +120,27 @@ namespace sb
 		(void)smem_scratch_word;
 #endif
 	}
+	// 32-byte store (STG.E.256, sm_100): a thread that owns 32 contiguous bytes writes a whole sector in one instruction
+	// instead of two half-sector writes.  p must be 32-byte aligned.
+	__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b)
+	{
+#ifndef STENOS_EMU
+		asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#else
+		reinterpret_cast<uint4*>(p)[0] = a;
+		reinterpret_cast<uint4*>(p)[1] = b;
+#endif
+	}
+	// 32-byte load (LDG.E.256, sm_100).  p must be 32-byte aligned.
+	__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b)
+	{
+#ifndef STENOS_EMU
+		asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#else
+		a = reinterpret_cast<const uint4*>(p)[0];
+		b = reinterpret_cast<const uint4*>(p)[1];
+#endif
+	}
 	__device__ __forceinline__ void prefetch_l2(const void* p)
 	{
 #ifndef STENOS_EMU

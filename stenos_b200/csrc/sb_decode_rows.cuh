@@ -274,6 +274,15 @@ namespace sb
 			}
 		}
 		uint4* dst = reinterpret_cast<uint4*>(block + (size_t)r * 16 * T);
+#if !defined(DECODE_STORE_128)
+		if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+			// whole 32-byte sectors per instruction (STG.E.256): the lane's 16 * T bytes are contiguous
+#pragma unroll
+			for (int i = 0; i < T; i += 2)
+				st_global_256(dst + i, make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]), make_uint4(e[4 * i + 4], e[4 * i + 5], e[4 * i + 6], e[4 * i + 7]));
+			return;
+		}
+#endif
 #pragma unroll
 		for (int i = 0; i < T; ++i) {
 			const uint4 v = make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);

@@ -157,13 +157,34 @@ namespace sb
 	{
 		const uint4* src = reinterpret_cast<const uint4*>(block + (size_t)r * 16 * T);
 		uint32_t e[4 * T];
+#if !defined(ENCODE_LOAD_128)
+		if ((reinterpret_cast<uintptr_t>(src) & 31u) == 0) {
+			// the row's 16 * T bytes are contiguous: whole 32-byte sectors per instruction (LDG.E.256)
 #pragma unroll
-		for (int i = 0; i < T; ++i) {
-			const uint4 v = src[i];
-			e[4 * i + 0] = v.x;
-			e[4 * i + 1] = v.y;
-			e[4 * i + 2] = v.z;
-			e[4 * i + 3] = v.w;
+			for (int i = 0; i < T; i += 2) {
+				uint4 a, b;
+				ld_global_256(src + i, a, b);
+				e[4 * i + 0] = a.x;
+				e[4 * i + 1] = a.y;
+				e[4 * i + 2] = a.z;
+				e[4 * i + 3] = a.w;
+				e[4 * i + 4] = b.x;
+				e[4 * i + 5] = b.y;
+				e[4 * i + 6] = b.z;
+				e[4 * i + 7] = b.w;
+			}
+		}
+		else
+#endif
+		{
+#pragma unroll
+			for (int i = 0; i < T; ++i) {
+				const uint4 v = src[i];
+				e[4 * i + 0] = v.x;
+				e[4 * i + 1] = v.y;
+				e[4 * i + 2] = v.z;
+				e[4 * i + 3] = v.w;
+			}
 		}
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {

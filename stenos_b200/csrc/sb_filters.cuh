@@ -115,6 +115,23 @@ namespace sb
 		}
 	}
 
+	// a thread's 16 elements (16 * T contiguous bytes, 16-byte aligned): whole 32-byte sectors per instruction when aligned
+	template<int T>
+	__device__ __forceinline__ void store_elements16(uint8_t* d, const uint32_t (&w)[4 * T])
+	{
+		if ((reinterpret_cast<uintptr_t>(d) & 31u) == 0) {
+#pragma unroll
+			for (int i = 0; i < T; i += 2)
+				st_global_256(d + 16 * i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]), make_uint4(w[4 * i + 4], w[4 * i + 5], w[4 * i + 6], w[4 * i + 7]));
+		}
+		else {
+			uint4* d4 = reinterpret_cast<uint4*>(d);
+#pragma unroll
+			for (int i = 0; i < T; ++i)
+				d4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+		}
+	}
+
 	// byte delta of a 16-byte vector given the byte that precedes it
 	__device__ __forceinline__ uint4 delta16(uint4 v, uint32_t before)
 	{
@@ -262,10 +279,7 @@ namespace sb
 				pl[k] = *reinterpret_cast<const uint4*>(src + (uint64_t)k * n + j0);
 			uint32_t w[4 * T];
 			untranspose16<T>(pl, w);
-			uint4* d4 = reinterpret_cast<uint4*>(dst + j0 * T);
-#pragma unroll
-			for (int i = 0; i < T; ++i)
-				d4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+			store_elements16<T>(dst + j0 * T, w);
 		}
 		else {
 			const uint64_t j1 = min(j0 + 16, n);
@@ -538,10 +552,7 @@ namespace sb
 			if (live) {
 				uint32_t w[4 * T];
 				untranspose16<T>(pl, w);
-				uint4* d4 = reinterpret_cast<uint4*>(dst + j0 * T);
-#pragma unroll
-				for (int i = 0; i < T; ++i)
-					d4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+				store_elements16<T>(dst + j0 * T, w);
 			}
 		}
 	}
