@@ -8,6 +8,7 @@
 // as well -- here through dlopen("libzstd.so.1").
 #include "sb_kernels.cuh"
 #include "sb_stream.cuh"
+#include "sb_flow.cuh"
 #include "sb_decode_rows.cuh"
 #include "sb_decode_split.cuh"
 #include "sb_filters.cuh"
@@ -15,6 +16,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -319,6 +321,40 @@ namespace
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
+#ifndef FLOW_THREADS_2
+#define FLOW_THREADS_2 512
+#endif
+#ifndef FLOW_THREADS_4
+#define FLOW_THREADS_4 512
+#endif
+#ifndef FLOW_THREADS_8
+#define FLOW_THREADS_8 256
+#endif
+	// encode_flow_kernel (sb_flow.cuh): the default fast path
+	template<int T, int NT>
+	size_t launch_flow_T(stenos_context* ctx, const EncodeParams& P)
+	{
+		const uint32_t smem = FlowLayout<T, NT>::smem_bytes();
+		if (cudaFuncSetAttribute((const void*)encode_flow_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_ALLOC;
+		}
+		// persistent CTAs, one per SM (the staging rings take the SM's shared memory); superblocks by ticket
+		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_stream, ctx->sm_count));
+		auto kern = encode_flow_kernel<T, NT>;
+#ifdef STENOS_EMU
+		if (getenv("STENOS_EMU_TRACE"))
+			fprintf(stderr, "encode_flow_kernel<%d,%d> grid %u n_stream %u n_sb %u\n", T, NT, grid, P.n_stream, P.n_sb);
+#endif
+		STENOS_LAUNCH(kern, dim3(grid), dim3(NT + 32), smem, ctx->stream(), P); // + the placer warp
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+	bool use_stream_v1()
+	{
+		static const bool v = [] { const char* e = getenv("STENOS_B200_ENCODER"); return e && e[0] == '1'; }(); // experiments: the round-1 pipeline
+		return v;
+	}
 	template<int T, int NT>
 	size_t launch_stream_T(stenos_context* ctx, const EncodeParams& P)
 	{
@@ -353,10 +389,11 @@ namespace
 		P.first_sb = n_stream;
 		size_t r = 0;
 		if (n_stream) {
+			const bool v1 = use_stream_v1();
 			switch (T) {
-				case 2: r = launch_stream_T<2, STREAM_THREADS_2>(ctx, P); break;
-				case 4: r = launch_stream_T<4, STREAM_THREADS_4>(ctx, P); break;
-				case 8: r = launch_stream_T<8, STREAM_THREADS_8>(ctx, P); break;
+				case 2: r = v1 ? launch_stream_T<2, STREAM_THREADS_2>(ctx, P) : launch_flow_T<2, FLOW_THREADS_2>(ctx, P); break;
+				case 4: r = v1 ? launch_stream_T<4, STREAM_THREADS_4>(ctx, P) : launch_flow_T<4, FLOW_THREADS_4>(ctx, P); break;
+				case 8: r = v1 ? launch_stream_T<8, STREAM_THREADS_8>(ctx, P) : launch_flow_T<8, FLOW_THREADS_8>(ctx, P); break;
 				default: return STENOS_ERROR_INVALID_PARAMETER;
 			}
 			if (is_err(r) || n_stream == P.n_sb)
