@@ -36,7 +36,33 @@ namespace sb
 #ifndef FLOW_STAGING
 #define FLOW_STAGING 2
 #endif
+	// waits of the flow kernel that last microseconds (ring space, a free slot, a placement): the polling warp must not
+	// compete for issue slots with the warps that encode (__nanosleep returns well before its nominal time)
+#ifdef STENOS_EMU
+#define FLOW_LONG_WAIT() emu::yield()
+#else
+#ifndef FLOW_LONG_WAIT_NS
+#define FLOW_LONG_WAIT_NS 1000
+#endif
+#define FLOW_LONG_WAIT() __nanosleep(FLOW_LONG_WAIT_NS)
+#endif
+	// Row decision table (find_pack_bits_params, block_compress.h:334-352, :420-435, :499-502): indexed by the row's value
+	// range (clipped to 32: everything above needs 8 bits) and delta range (clipped to 64), an entry holds
+	// header nibble | payload bytes << 4 | row size << 9 | plain << 14 -- one LDS instead of ~25 integer instructions.
+	constexpr uint32_t FLOW_HLUT_RB = 33, FLOW_HLUT_RD = 65, FLOW_HLUT_N = FLOW_HLUT_RB * FLOW_HLUT_RD;
+	__device__ __forceinline__ uint32_t flow_hlut_entry(uint32_t rb, uint32_t rd)
+	{
+		const uint32_t b0 = rb >= 32u ? 8u : (32u - (uint32_t)__clz((int)rb)); // 7 -> 8, and 6 -> 8 for the plain type
+		const uint32_t b1 = rd >= 64u ? 8u : (32u - (uint32_t)__clz((int)rd));
+		const uint32_t bits = min(b0, b1);
+		const bool plain = (b0 == bits); // ties -> plain
+		const uint32_t sz = 2u * bits + (bits != 8u ? 1u : 0u);
+		const uint32_t h = plain ? (bits == 8u ? 15u : bits) : (8u + bits);
+		const uint32_t pay = (bits == 8u) ? 16u : 2u * bits;
+		return h | (pay << 4) | (sz << 9) | ((plain ? 1u : 0u) << 14);
+	}
 	constexpr int FLOW_NS = 8;  // superblocks in flight per CTA
+	constexpr int FLOW_PQ = 8;   // pieces a half-warp may have waiting for their placement
 	constexpr int FLOW_SBQ = 16; // ring of superblock numbers handed to the CTA (> FLOW_NS + 1)
 
 	template<int T, int NT>
@@ -55,9 +81,12 @@ namespace sb
 		static constexpr uint32_t SLOT_BYTES = 64u + NH * 8u;
 		static constexpr uint32_t CTL_OFF = 0;                 // sbq[FLOW_SBQ] u64
 		static constexpr uint32_t SLOT_OFF = FLOW_SBQ * 8u;
-		static constexpr uint32_t PINFO_OFF = SLOT_OFF + FLOW_NS * SLOT_BYTES; // [NH][FLOW_NS] x 16 bytes
-		static constexpr uint32_t LUT_OFF = PINFO_OFF + NH * FLOW_NS * 16u;
-		static constexpr uint32_t TAIL_OFF = LUT_OFF + 1024u;
+		static constexpr uint32_t PINFO_OFF = SLOT_OFF + FLOW_NS * SLOT_BYTES; // [NH][FLOW_PQ] x 16 bytes: pieces waiting for their placement
+		static constexpr uint32_t PMETA_OFF = PINFO_OFF + NH * FLOW_PQ * 16u;   // [NW][FLOW_PQ] x 4 bytes: their task numbers
+		static constexpr uint32_t TASK_OFF = PMETA_OFF + NW * FLOW_PQ * 4u;     // the CTA's task counter
+		static constexpr uint32_t LUT_OFF = TASK_OFF + 16u;
+		static constexpr uint32_t HLUT_OFF = LUT_OFF + 1024u; // row decision table, FLOW_HLUT_N x u16
+		static constexpr uint32_t TAIL_OFF = HLUT_OFF + ((FLOW_HLUT_N * 2u + 15u) & ~15u);
 		static constexpr uint32_t LZ_OFF = TAIL_OFF + TMP;
 		static constexpr uint32_t IN_OFF = LZ_OFF + HAS_LZ * NW * LZ_STRIDE; // per warp: the rows of the block pair that comes next (cp.async)
 		static constexpr uint32_t IN_STRIDE = FLOW_STAGING == 2 ? 32u * 16u * T : 0u;
@@ -137,6 +166,20 @@ namespace sb
 		}
 	}
 
+	// one step of an inclusive scan inside 16-lane segments: v += (v of the lane `delta` below, if it is in my segment);
+	// the shuffle's own in-range predicate guards the add (no compare, no select)
+	__device__ __forceinline__ uint32_t scan_up16_step(uint32_t v, int delta, int r)
+	{
+#ifdef STENOS_EMU
+		const uint32_t t = __shfl_up_sync(FULL, v, delta, 16);
+		return r >= delta ? v + t : v;
+#else
+		(void)r;
+		asm("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0x1000, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(v) : "r"(delta));
+		return v;
+#endif
+	}
+
 	// ------------------------------------------------------------------------------------------
 	// row payload helpers
 	// ------------------------------------------------------------------------------------------
@@ -168,8 +211,15 @@ namespace sb
 	// of 8 values of `bits` bytes each are one contiguous string of 16 * bits bits)
 	__device__ __forceinline__ void flow_pack_row(const uint32_t (&v)[4], uint32_t bits, uint32_t (&w)[4])
 	{
-		const uint32_t mul = 1u << bits;
-		const uint32_t p0 = pack4_mul(v[0], mul), p1 = pack4_mul(v[1], mul), p2 = pack4_mul(v[2], mul), p3 = pack4_mul(v[3], mul);
+		const uint32_t mul = 1u << bits, mul2 = mul * mul;
+		uint32_t pk[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			// [v0 | v1 << bits] and [v2 | v3 << bits] in the two 16-bit lanes, then the two lanes joined
+			const uint32_t c = __byte_perm(v[j], 0u, 0x4341) * mul + __byte_perm(v[j], 0u, 0x4240);
+			pk[j] = __byte_perm(c, 0u, 0x4432) * mul2 + __byte_perm(c, 0u, 0x4410);
+		}
+		const uint32_t p0 = pk[0], p1 = pk[1], p2 = pk[2], p3 = pk[3];
 		const uint32_t s = 4u * bits; // 4..24
 		const uint32_t g0l = p0 | (p1 << s), g0h = p1 >> (32u - s);
 		const uint32_t g1l = p2 | (p3 << s), g1h = p3 >> (32u - s);
@@ -209,7 +259,7 @@ namespace sb
 	// Returns the plane's size; kind through kind_out (both uniform over the half-warp).
 	// ------------------------------------------------------------------------------------------
 	__device__ __forceinline__ uint32_t flow_plane(uint32_t o, const uint32_t (&a)[4], uint32_t pvw, bool half_same, bool emit, int r, uint32_t hsh, const uint32_t* lut,
-						      uint32_t& kind_out)
+						      const uint16_t* hlut, uint32_t& kind_out)
 	{
 		// ---- row statistics (:399-474)
 		uint32_t d[4];
@@ -220,15 +270,13 @@ namespace sb
 		const uint32_t MN = __vmins2(prmt_sx(mnv, mnd, 0xD591), prmt_sx(mnv, mnd, 0xF7B3)); // [values | deltas] as s16x2
 		const uint32_t MX = __vmaxs2(prmt_sx(mxv, mxd, 0xD591), prmt_sx(mxv, mxd, 0xF7B3));
 		const uint32_t R = __vsub2(MX, MN);
-		const uint32_t rb = R & 0xFFFFu, rd = R >> 16;
-		const uint32_t b0 = rb >= 32u ? 8u : (32u - (uint32_t)__clz((int)rb)); // :334-352, :420-423
-		const uint32_t b1 = rd >= 64u ? 8u : (32u - (uint32_t)__clz((int)rd));
-		const uint32_t bits = min(b0, b1);
-		const bool plain = (b0 == bits);
+		// bit widths, type, size and header nibble of the row (:334-352, :420-435, :499-502) from the decision table
+		const uint32_t hent = hlut[min(R & 0xFFFFu, FLOW_HLUT_RB - 1u) + min(R >> 16, FLOW_HLUT_RD - 1u) * FLOW_HLUT_RB];
+		const bool plain = (hent >> 14) != 0u;
 		const uint32_t minv = (plain ? MN : (MN >> 16)) & 0xFFu;
-		uint32_t sz = 2u * bits + (bits != 8u ? 1u : 0u);            // :433-435
-		uint32_t h = plain ? (bits == 8u ? 15u : bits) : (8u + bits); // :499-502
-		uint32_t pay = (bits == 8u) ? 16u : 2u * bits;
+		uint32_t sz = (hent >> 9) & 31u;
+		uint32_t h = hent & 15u;
+		uint32_t pay = (hent >> 4) & 31u;
 		uint32_t x[4], nzd[4], nzx[4];
 		delta_repeats(d, x);
 		uint32_t nr = 0, nd = 0;
@@ -257,11 +305,8 @@ namespace sb
 		// stored mins (bits 10..14) of the rows before mine
 		uint32_t incl = pay | (needmin ? 1024u : 0u);
 #pragma unroll
-		for (int dlt = 1; dlt < 16; dlt <<= 1) {
-			const uint32_t t = __shfl_up_sync(FULL, incl, dlt, 16);
-			if (r >= dlt)
-				incl += t;
-		}
+		for (int dlt = 1; dlt < 16; dlt <<= 1)
+			incl = scan_up16_step(incl, dlt, r);
 		const uint32_t tot = __shfl_sync(FULL, incl, 15, 16);
 		const uint32_t paysum = tot & 1023u, nmins = tot >> 10;
 		uint32_t hmp = __shfl_up_sync(FULL, h | (minv << 8), 1, 16); // the previous row's header nibble and min
@@ -359,7 +404,7 @@ namespace sb
 
 	template<int T, class Next>
 	__device__ __forceinline__ uint32_t flow_encode_block(const uint32_t (&e)[4 * T], const uint8_t* __restrict__ blk, bool active, uint8_t* sm, uint32_t out, uint32_t out32,
-							     uint32_t* lz_scratch, const uint32_t* lut, int lane, Next&& row_consumed)
+							     uint32_t* lz_scratch, const uint32_t* lut, const uint16_t* hlut, int lane, Next&& row_consumed)
 	{
 		constexpr uint32_t HS = (T + 1) / 2;
 		constexpr int NE = 4 * T;
@@ -398,6 +443,11 @@ namespace sb
 #pragma unroll
 		for (int g = 0; g < NG; ++g)
 			XA[g] = __reduce_or_sync(FULL, X[g]);
+#ifndef STENOS_EMU
+#pragma unroll
+		for (int g = 0; g < NG; ++g)
+			asm("" : "+r"(X[g])); // keeps X in its register (the compiler recomputed the 16-LOP3 chain for every plane instead)
+#endif
 		row_consumed(); // every word of the row has been read (XA depends on all of them): the input buffer may be refilled
 
 		uint32_t pos = HS, kinds = 0;
@@ -435,7 +485,7 @@ namespace sb
 				const uint32_t sm_ = __ballot_sync(FULL, ((X[g] >> sh8) & 0xFFu) == 0u);
 				const bool half_same = ((sm_ >> hsh) & 0xFFFFu) == 0xFFFFu;
 				uint32_t kind;
-				const uint32_t psz = flow_plane(out32 + pos, a, pvw, half_same, active, r, hsh, lut, kind);
+				const uint32_t psz = flow_plane(out32 + pos, a, pvw, half_same, active, r, hsh, lut, hlut, kind);
 				kinds |= kind << (4 * p);
 				pos += psz;
 			}
@@ -543,6 +593,7 @@ namespace sb
 		STENOS_DYN_SMEM(uint8_t, smem);
 		unsigned long long* sbq = reinterpret_cast<unsigned long long*>(smem + L::CTL_OFF); // (q + 1) << 32 | superblock of the CTA's q-th turn
 		uint32_t* lut = reinterpret_cast<uint32_t*>(smem + L::LUT_OFF);
+		uint16_t* hlut = reinterpret_cast<uint16_t*>(smem + L::HLUT_OFF);
 		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 		const int hb = lane >> 4, r = lane & 15;
 		const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
@@ -553,7 +604,7 @@ namespace sb
 		// follows a wait are warp collectives
 		auto wait_u32 = [&](const uint32_t* p, uint32_t want) {
 			while (__shfl_sync(FULL, ld_vol_u32(p), 0) != want)
-				STENOS_SPIN_WAIT();
+				FLOW_LONG_WAIT();
 		};
 
 		for (uint32_t i = tid; i < L::LUT_OFF / 4u; i += NT + 32)
@@ -566,6 +617,8 @@ namespace sb
 					sel |= b << (4u * k++);
 			lut[m] = sel;
 		}
+		for (uint32_t i = tid; i < FLOW_HLUT_N; i += NT + 32)
+			hlut[i] = (uint16_t)flow_hlut_entry(i % FLOW_HLUT_RB, i / FLOW_HLUT_RB);
 		__syncthreads();
 		if (tid == 0) {
 			for (uint32_t i = 0; i < (uint32_t)FLOW_NS; ++i)
@@ -608,11 +661,7 @@ namespace sb
 						const int fi = inc ? (__ffs((int)inc) - 1) : 32;
 						const uint32_t upto = fi >= 31 ? 0xFFFFFFFFu : ((2u << fi) - 1u);
 						if (inv & upto) {
-#ifdef FLOW_LOOKBACK_FAST
-							STENOS_SPIN_HINT();
-#else
 							STENOS_SPIN_WAIT();
-#endif
 							continue;
 						}
 						unsigned long long val = ((upto >> lane) & 1u) ? (v & LB_VALUE) : 0ull;
@@ -681,13 +730,20 @@ namespace sb
 		}
 
 		// ================================ the encoder warps ================================
+		// A TASK is a pair of adjacent pieces of one superblock (one piece per half-warp).  Warps take tasks from a counter
+		// in shared memory, in order: t -> the CTA's turn q = t / NW, pair j = t % NW.  (Static pieces per warp were measured
+		// first: a warp that runs a little slower -- more warps on its scheduler, a spinning neighbour -- fell turns behind,
+		// the fast ones ran ahead until their rings were full, the superblock tickets they had taken sat unencoded and
+		// every placement behind them waited: 40 % of the warps' time went into waiting for ring space.)
 		const uint32_t half = 2u * (uint32_t)warp + (uint32_t)hb;
 		uint32_t* lz_scratch = reinterpret_cast<uint32_t*>(smem + L::LZ_OFF + L::LZ_STRIDE * (L::HAS_LZ ? warp : 0));
 		const uint32_t stage = L::STAGE_OFF + half * L::REG; // my half-warp's staging ring
-		uint32_t* pinfo = reinterpret_cast<uint32_t*>(smem + L::PINFO_OFF) + half * (FLOW_NS * 4u);
+		uint32_t* pinfo = reinterpret_cast<uint32_t*>(smem + L::PINFO_OFF) + half * (FLOW_PQ * 4u);
+		uint32_t* pmeta = reinterpret_cast<uint32_t*>(smem + L::PMETA_OFF) + (uint32_t)warp * FLOW_PQ;
+		uint32_t* task_ctr = reinterpret_cast<uint32_t*>(smem + L::TASK_OFF);
 		const uint32_t nblk_sb = P.sb_bytes / L::BLOCK;
 		const uint32_t K = max(1u, (nblk_sb + L::NH - 1u) / L::NH); // blocks per piece
-		uint32_t q = 0, pend_lo = 0;
+		uint32_t pq_head = 0, pq_tail = 0;     // my warp's pieces waiting for their placement: entries [pq_head, pq_tail) mod FLOW_PQ
 		uint32_t pos = 0, vcur = 0, vtail = 0; // my half's ring: write position, and monotonic counters of bytes claimed / released
 		const uint32_t stage32 = smem_addr32(smem) + stage;
 		const uint32_t in32 = smem_addr32(smem) + L::IN_OFF + (uint32_t)warp * L::IN_STRIDE; // my warp's input rows (FLOW_STAGING 2)
@@ -699,15 +755,28 @@ namespace sb
 			e[i] = 0u;
 		bool have = false;
 
-		// copies my half's piece of the CTA's superblock turn qo to the frame and releases its ring space and slot
-		auto drain_one = [&](uint32_t qo) {
+		auto take_task = [&]() {
+			uint32_t t = 0;
+			if (lane == 0)
+				t = atomicAdd(task_ctr, 1u);
+			return __shfl_sync(FULL, t, 0);
+		};
+		// is the oldest waiting piece placed?  (decided by lane 0 for the warp)
+		auto head_ready = [&]() {
+			const uint32_t qo = ld_vol_u32(pmeta + pq_head % FLOW_PQ) / L::NW;
+			return __shfl_sync(FULL, ld_vol_u32(&slot_of(qo)->ready), 0) == qo + 1u;
+		};
+		// copies my half's oldest waiting piece to the frame and releases its ring space (blocks until it is placed)
+		auto drain_one = [&]() {
+			const uint32_t to_ = ld_vol_u32(pmeta + pq_head % FLOW_PQ);
+			const uint32_t qo = to_ / L::NW, jo = to_ % L::NW;
 			FlowSlot* sl = slot_of(qo);
 			wait_u32(&sl->ready, qo + 1u);
 			__threadfence_block();
 			const uint32_t mode = ld_vol_u32(&sl->mode);
 			const unsigned long long base = *reinterpret_cast<volatile unsigned long long*>(&sl->base);
-			const uint32_t pi = 2u * (((uint32_t)warp + qo) % L::NW) + (uint32_t)hb;
-			const uint32_t* pf = pinfo + (qo % FLOW_NS) * 4u;
+			const uint32_t pi = 2u * jo + (uint32_t)hb;
+			const uint32_t* pf = pinfo + (pq_head % FLOW_PQ) * 4u;
 			const uint32_t posA = ld_vol_u32(pf + 0), lenA = ld_vol_u32(pf + 1), lenB = ld_vol_u32(pf + 2), vend = ld_vol_u32(pf + 3);
 			if (mode == 0u) {
 				uint8_t* to = P.dst + base + 4u + ld_vol_u32(offs_of(sl) + pi);
@@ -730,8 +799,7 @@ namespace sb
 			if (lane == 0) {
 				const uint32_t old = atomicAdd(&sl->consumed, 1u);
 				if (old == L::NW - 1u) {
-					// every warp is done with this superblock: the slot goes to turn qo + FLOW_NS
-					sl->started = 0u;
+					// every task of this superblock has left: the slot goes to turn qo + FLOW_NS
 					sl->arrived = 0u;
 					sl->consumed = 0u;
 					__threadfence_block();
@@ -739,9 +807,12 @@ namespace sb
 				}
 			}
 			__syncwarp();
+			++pq_head;
 		};
 
+		uint32_t t = take_task();
 		for (;;) {
+			const uint32_t q = t / L::NW, j = t % L::NW;
 			// ---- the CTA's q-th superblock
 			unsigned long long tk;
 			while (((tk = __shfl_sync(FULL, *reinterpret_cast<volatile unsigned long long*>(&sbq[q % FLOW_SBQ]), 0)) >> 32) != q + 1u)
@@ -749,69 +820,74 @@ namespace sb
 			const uint32_t s = (uint32_t)tk;
 			if (s >= P.n_stream)
 				break; // superblocks are handed out in increasing order: this CTA has no further work
+			if (j == L::NW / 2u && lane == 0) {
+				// The CTA's next superblock is asked for half a turn ahead: early enough that its number is there when the first
+				// task of the next turn starts, late enough that the ticket does not sit unencoded for long (every superblock
+				// handed out and not yet encoded holds up the placement of all later ones).
+				const uint32_t nx = atomicAdd(P.ticket + 1, 1u);
+				*reinterpret_cast<volatile unsigned long long*>(&sbq[(q + 1u) % FLOW_SBQ]) = ((unsigned long long)(q + 2u) << 32) | nx;
+			}
 			FlowSlot* slot = slot_of(q);
 			while (__shfl_sync(FULL, ld_vol_u32(&slot->owner), 0) != q + 1u) {
 				// the slot is still held by turn q - FLOW_NS: somebody (maybe me) has not copied that superblock out yet
-				if (pend_lo < q && __shfl_sync(FULL, ld_vol_u32(&slot_of(pend_lo)->ready), 0) == pend_lo + 1u) {
-					drain_one(pend_lo);
-					++pend_lo;
-				}
+				if (pq_head != pq_tail && head_ready())
+					drain_one();
 				else
-					STENOS_SPIN_WAIT();
-			}
-			if (lane == 0 && atomicAdd(&slot->started, 1u) == 0u) {
-				// first warp to get here: fetch the CTA's next superblock, one superblock ahead of its first use
-				const uint32_t nx = atomicAdd(P.ticket + 1, 1u);
-				*reinterpret_cast<volatile unsigned long long*>(&sbq[(q + 1u) % FLOW_SBQ]) = ((unsigned long long)(q + 2u) << 32) | nx;
+					FLOW_LONG_WAIT();
 			}
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
 			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
 			const uint32_t nfull = in_bytes / L::BLOCK;
-			const uint32_t pi = 2u * (((uint32_t)warp + q) % L::NW) + (uint32_t)hb; // my piece (rotated so that no warp always gets the same part)
+			const uint32_t pi = 2u * j + (uint32_t)hb; // my half's piece
 			const uint32_t b0 = pi * K;
 			const uint32_t cnt = b0 < nfull ? min(K, nfull - b0) : 0u;
 			const uint8_t* blk = in + (uint64_t)b0 * L::BLOCK;
+			while (pq_tail - pq_head >= (uint32_t)FLOW_PQ)
+				drain_one(); // no entry left for this piece
 
 			uint32_t posA = pos, lenA = 0, lenB = 0;
 			bool wrapped = false;
-			for (uint32_t it = 0; it < K; ++it) {
+			uint32_t tnext = 0xFFFFFFFFu; // my warp's next task, taken during the last block of this one
+			const uint32_t kmax = max(1u, __reduce_max_sync(FULL, cnt));
+			for (uint32_t it = 0; it < kmax; ++it) {
 				const bool active = it < cnt;
-				if (!__any_sync(FULL, active))
-					break;
 				if (active && pos + L::MAXB > L::REG) {
 					// a block never wraps: the piece continues at the start of the ring
 					vcur += L::REG - pos;
 					pos = 0;
 					wrapped = true;
 				}
-				while (__any_sync(FULL, active && vcur + L::MAXB - vtail > L::REG)) {
-					// no room: my oldest piece still in the ring has to leave first
-					drain_one(pend_lo);
-					++pend_lo;
-				}
+				while (__any_sync(FULL, active && vcur + L::MAXB - vtail > L::REG))
+					drain_one(); // no room: my oldest piece still in the ring has to leave first
+				// pieces that were placed meanwhile leave for the frame
+				while (pq_head != pq_tail && head_ready())
+					drain_one();
+				if (it + 1u == kmax)
+					tnext = take_task();
 				const uint8_t* myblk = blk + (size_t)it * L::BLOCK;
-				// my half's next block: the next one of the piece, or the first one of my piece of the CTA's next superblock
+				// my half's next block: the next one of the piece, or the first one of my piece of the next task
 				const uint8_t* nb = nullptr;
 				if (it + 1u < cnt)
 					nb = myblk + L::BLOCK;
-				else if (it + 1u == max(cnt, 1u)) { // (later rounds of a half with fewer blocks keep what was fetched here)
-					const unsigned long long t2 = *reinterpret_cast<volatile unsigned long long*>(&sbq[(q + 1u) % FLOW_SBQ]);
+				else if (it + 1u == kmax) {
+					const uint32_t q2 = tnext / L::NW;
+					const unsigned long long t2 = *reinterpret_cast<volatile unsigned long long*>(&sbq[q2 % FLOW_SBQ]);
 					const uint32_t s2 = (uint32_t)t2;
-					if ((uint32_t)(t2 >> 32) == q + 2u && s2 < P.n_stream) {
+					if ((uint32_t)(t2 >> 32) == q2 + 1u && s2 < P.n_stream) {
 						const uint32_t nfull2 = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s2 * P.sb_bytes) / L::BLOCK;
-						const uint32_t b2 = (2u * (((uint32_t)warp + q + 1u) % L::NW) + (uint32_t)hb) * K;
+						const uint32_t b2 = (2u * (tnext % L::NW) + (uint32_t)hb) * K;
 						if (b2 < nfull2)
 							nb = P.src + (uint64_t)s2 * P.sb_bytes + (uint64_t)b2 * L::BLOCK;
 					}
 				}
-				const bool upd = it < max(cnt, 1u);
+				const bool upd = it + 1u < cnt || it + 1u == kmax; // (an idle round of a half with fewer blocks keeps what was fetched)
 #if FLOW_STAGING == 2
 				if (active && !have)
 					flow_fetch_row<T>(in32, myblk + (size_t)r * 16 * T, lane);
 				cp_async_commit(); // (wait_group only waits for committed copies)
 				cp_async_wait_all();
 				flow_read_row<T>(in32, lane, e);
-				const uint32_t sz = flow_encode_block<T>(e, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, lane, [&]() {
+				const uint32_t sz = flow_encode_block<T>(e, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, hlut, lane, [&]() {
 					if (upd) {
 						have = nb != nullptr;
 						if (have)
@@ -831,13 +907,13 @@ namespace sb
 					if (have)
 						flow_load_row<T>(nb, r, e);
 				}
-				const uint32_t sz = flow_encode_block<T>(cur, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, lane, []() {});
+				const uint32_t sz = flow_encode_block<T>(cur, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, hlut, lane, []() {});
 #else
 				if (nb != nullptr && ((uint32_t)r * 16u * T) % 128u == 0u)
 					prefetch_l2(nb + (size_t)r * 16 * T);
 				if (active)
 					flow_load_row<T>(myblk, r, e);
-				const uint32_t sz = flow_encode_block<T>(e, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, lane, []() {});
+				const uint32_t sz = flow_encode_block<T>(e, myblk, active, smem, stage + pos, stage32 + pos, lz_scratch, lut, hlut, lane, []() {});
 #endif
 				pos += sz;
 				vcur += sz;
@@ -849,13 +925,16 @@ namespace sb
 
 			// ---- publish my piece; the placer puts the superblock in the frame once all pieces are there
 			if (r == 0) {
-				uint32_t* pf = pinfo + (q % FLOW_NS) * 4u;
+				uint32_t* pf = pinfo + (pq_tail % FLOW_PQ) * 4u;
 				st_vol_u32(pf + 0, posA);
 				st_vol_u32(pf + 1, lenA);
 				st_vol_u32(pf + 2, lenB);
 				st_vol_u32(pf + 3, vcur);
 				st_vol_u32(sizes_of(slot) + pi, lenA + lenB);
 			}
+			if (lane == 0)
+				st_vol_u32(pmeta + pq_tail % FLOW_PQ, t);
+			++pq_tail;
 			__syncwarp();
 			__threadfence_block();
 			uint32_t na = 0;
@@ -863,7 +942,7 @@ namespace sb
 				na = atomicAdd(&slot->arrived, 1u);
 			na = __shfl_sync(FULL, na, 0);
 			if (na == L::NW - 1u) {
-				// Last piece of the superblock: exclusive scan of the piece sizes, and the superblock's size goes out as the
+				// Last task of the superblock: exclusive scan of the piece sizes, and the superblock's size goes out as the
 				// AGGREGATE word of the look-back right away -- successors must never wait for this CTA's placer, which may
 				// itself be waiting for a predecessor (measured: with the placer publishing it, placers spun ~100 % of the time).
 				__threadfence_block();
@@ -880,9 +959,9 @@ namespace sb
 				uint32_t incl = sum;
 #pragma unroll
 				for (int dlt = 1; dlt < 32; dlt <<= 1) {
-					const uint32_t t = __shfl_up_sync(FULL, incl, dlt);
+					const uint32_t tt = __shfl_up_sync(FULL, incl, dlt);
 					if (lane >= dlt)
-						incl += t;
+						incl += tt;
 				}
 				uint32_t run = incl - sum;
 #pragma unroll
@@ -898,8 +977,8 @@ namespace sb
 				const uint32_t tail_off = csize;
 				uint32_t tail_sz = 0;
 				if (rem) {
-					bool e = false;
-					tail_sz = encode_partial_block<T, false>(in + (size_t)nfull * L::BLOCK, rem, smem + L::TAIL_OFF, lane, 0xFFFFFFFFu, e);
+					bool e2 = false;
+					tail_sz = encode_partial_block<T, false>(in + (size_t)nfull * L::BLOCK, rem, smem + L::TAIL_OFF, lane, 0xFFFFFFFFu, e2);
 					__syncwarp();
 					csize += tail_sz;
 				}
@@ -914,17 +993,10 @@ namespace sb
 				}
 				__syncwarp();
 			}
-			++q;
-			// ---- superblocks that were placed meanwhile: my pieces of them leave for the frame
-			while (pend_lo < q && __shfl_sync(FULL, ld_vol_u32(&slot_of(pend_lo)->ready), 0) == pend_lo + 1u) {
-				drain_one(pend_lo);
-				++pend_lo;
-			}
+			t = tnext;
 		}
-		while (pend_lo < q) {
-			drain_one(pend_lo);
-			++pend_lo;
-		}
+		while (pq_head != pq_tail)
+			drain_one();
 #if FLOW_STAGING == 2
 		cp_async_wait_all();
 #endif
