@@ -160,6 +160,9 @@ STENOS_B200_EXPORT size_t stenos_b200_gather_decode_async(stenos_context* ctx, c
 
 /* Waits for the context's stream. */
 STENOS_B200_EXPORT size_t stenos_b200_synchronize(stenos_context* ctx);
+/* Test support: keeps `ctas` SMs busy (one CTA holding smem_kb KiB of shared memory each) for about `ns` nanoseconds
+ * on the given stream, so that a test can launch the encoder next to a kernel that leaves it only a few SMs. */
+STENOS_B200_EXPORT size_t stenos_b200_test_occupy(void* cuda_stream, int ctas, unsigned smem_kb, unsigned long long ns);
 /* Number of kernels this library has launched in the process (bench.py reports it as gpu_launches). */
 STENOS_B200_EXPORT unsigned long long stenos_b200_kernel_launches(void);
 /* "sm_100a" for the product build, "emu" for the CPU test build of tests/emu. */

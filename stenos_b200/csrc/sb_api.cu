@@ -145,7 +145,7 @@ struct stenos_context_s
 	size_t superblock = 0;
 	int shift = 0;
 	// scratch
-	DevBuf in, out, ctl, idx, scan, dtk, blk;
+	DevBuf in, out, ctl, idx, scan, dtk, blk, spill;
 	bool serial_index = false; // tests: force the serial header walk
 	bool legacy_encoder = false; // tests: every superblock through encode_frame_kernel
 	bool legacy_decoder = false;
@@ -157,6 +157,25 @@ struct stenos_context_s
 	cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
 	cudaEvent_t pipe_ev[2 * PIPE_MAX] = {};
 	unsigned long long* pipe_host = nullptr; // pinned, 2 words per chunk
+	unsigned long long* pipe_offs = nullptr; // pinned: superblock offsets of a host frame (pipelined decompress)
+	size_t pipe_offs_cap = 0;
+	bool pipe_offs_reserve(size_t n)
+	{
+		if (n <= pipe_offs_cap)
+			return true;
+		if (pipe_offs)
+			cudaFreeHost(pipe_offs);
+		pipe_offs = nullptr;
+		pipe_offs_cap = 0;
+		const size_t want = n + (n >> 2) + 64;
+		if (cudaMallocHost((void**)&pipe_offs, want * 8) != cudaSuccess) {
+			cudaGetLastError();
+			pipe_offs = nullptr;
+			return false;
+		}
+		pipe_offs_cap = want;
+		return true;
+	}
 	DevBuf pipe_res;                         // 2 words per chunk
 	bool pipe_ready = false;
 	bool pipe_init()
@@ -255,12 +274,17 @@ struct stenos_context_s
 		scan.release();
 		dtk.release();
 		blk.release();
+		spill.release();
 		if (host_result)
 			cudaFreeHost(host_result);
 		host_result = nullptr;
 		if (pipe_host)
 			cudaFreeHost(pipe_host);
 		pipe_host = nullptr;
+		if (pipe_offs)
+			cudaFreeHost(pipe_offs);
+		pipe_offs = nullptr;
+		pipe_offs_cap = 0;
 		for (int i = 0; i < 2 * PIPE_MAX; ++i)
 			if (pipe_ev[i]) {
 				cudaEventDestroy(pipe_ev[i]);
@@ -322,31 +346,49 @@ namespace
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 #ifndef FLOW_THREADS_2
-#define FLOW_THREADS_2 512
+#define FLOW_THREADS_2 608
 #endif
 #ifndef FLOW_THREADS_4
-#define FLOW_THREADS_4 512
+#define FLOW_THREADS_4 576
 #endif
 #ifndef FLOW_THREADS_8
-#define FLOW_THREADS_8 256
+#define FLOW_THREADS_8 352
+#endif
+	// blocks per piece (a task = two pieces)
+#ifndef FLOW_KB_2
+#define FLOW_KB_2 8
+#endif
+#ifndef FLOW_KB_4
+#define FLOW_KB_4 3
+#endif
+#ifndef FLOW_KB_8
+#define FLOW_KB_8 2
 #endif
 	// encode_flow_kernel (sb_flow.cuh): the default fast path
-	template<int T, int NT>
+	template<int T, int NT, int KB>
 	size_t launch_flow_T(stenos_context* ctx, const EncodeParams& P)
 	{
-		const uint32_t smem = FlowLayout<T, NT>::smem_bytes();
-		if (cudaFuncSetAttribute((const void*)encode_flow_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+		const uint32_t smem = FlowLayout<T, NT, KB>::smem_bytes();
+		if (cudaFuncSetAttribute((const void*)encode_flow_kernel<T, NT, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
 			cudaGetLastError();
 			return STENOS_ERROR_ALLOC;
 		}
 		// persistent CTAs, one per SM (the staging rings take the SM's shared memory); superblocks by ticket
 		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_stream, ctx->sm_count));
-		auto kern = encode_flow_kernel<T, NT>;
+		if (!ctx->spill.reserve(FlowLayout<T, NT, KB>::spill_bytes(grid)))
+			return STENOS_ERROR_ALLOC;
+		EncodeParams Q = P;
+		Q.spill = ctx->spill.p;
+		{
+			const char* e = getenv("STENOS_B200_FLOW_RING"); // tests: staging ring bytes (clamped to the legal minimum): forces the spill path
+			Q.ring_cap = e ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
+		}
+		auto kern = encode_flow_kernel<T, NT, KB>;
 #ifdef STENOS_EMU
 		if (getenv("STENOS_EMU_TRACE"))
 			fprintf(stderr, "encode_flow_kernel<%d,%d> grid %u n_stream %u n_sb %u\n", T, NT, grid, P.n_stream, P.n_sb);
 #endif
-		STENOS_LAUNCH(kern, dim3(grid), dim3(NT + 32), smem, ctx->stream(), P); // + the placer warp
+		STENOS_LAUNCH(kern, dim3(grid), dim3(NT + 32), smem, ctx->stream(), Q); // + the placer warp
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
@@ -391,9 +433,9 @@ namespace
 		if (n_stream) {
 			const bool v1 = use_stream_v1();
 			switch (T) {
-				case 2: r = v1 ? launch_stream_T<2, STREAM_THREADS_2>(ctx, P) : launch_flow_T<2, FLOW_THREADS_2>(ctx, P); break;
-				case 4: r = v1 ? launch_stream_T<4, STREAM_THREADS_4>(ctx, P) : launch_flow_T<4, FLOW_THREADS_4>(ctx, P); break;
-				case 8: r = v1 ? launch_stream_T<8, STREAM_THREADS_8>(ctx, P) : launch_flow_T<8, FLOW_THREADS_8>(ctx, P); break;
+				case 2: r = v1 ? launch_stream_T<2, STREAM_THREADS_2>(ctx, P) : launch_flow_T<2, FLOW_THREADS_2, FLOW_KB_2>(ctx, P); break;
+				case 4: r = v1 ? launch_stream_T<4, STREAM_THREADS_4>(ctx, P) : launch_flow_T<4, FLOW_THREADS_4, FLOW_KB_4>(ctx, P); break;
+				case 8: r = v1 ? launch_stream_T<8, STREAM_THREADS_8>(ctx, P) : launch_flow_T<8, FLOW_THREADS_8, FLOW_KB_8>(ctx, P); break;
 				default: return STENOS_ERROR_INVALID_PARAMETER;
 			}
 			if (is_err(r) || n_stream == P.n_sb)
@@ -637,6 +679,8 @@ namespace
 		P.result = d_result ? d_result : c.result;
 		P.sb_offsets = d_sb_offsets;
 		P.base_offset = 0;
+		P.spill = nullptr;
+		P.ring_cap = 0;
 		return launch_encode(ctx, T, P);
 	}
 
@@ -1010,6 +1054,86 @@ namespace
 		cudaMemsetAsync(d_result, 0, 16, st);
 		unsigned last_code = 0;
 		size_t last_at = 0, last_csize = 0;
+
+		// ---- host -> host through the device, pipelined (stenos.cpp:1052-1208 on host buffers): the frame is cut in
+		// chunks of whole superblocks (32 MiB of output); the host walks the headers of chunk i + 1 (stenos.cpp:1124-1143)
+		// while the compressed bytes of chunk i are on the bus, the decoder runs on chunk i as soon as they have landed
+		// and its output leaves for the caller's buffer on a third stream while later chunks are decoded.
+		{
+			const char* pipe_env = getenv("STENOS_B200_PIPELINE_CHUNK");
+			const size_t pipe_chunk = pipe_env ? (size_t)strtoull(pipe_env, nullptr, 10) : ((size_t)32 << 20);
+			const size_t last_dsize0 = (size_t)(total - (uint64_t)(n_sb - 1) * sb);
+			if (frame && !src_dev && !dst_dev && pipe_chunk && total >= 2 * (uint64_t)pipe_chunk && last_dsize0 >= 128 && ctx->pipe_init()) {
+				size_t chunk_sb = std::max<size_t>(1, std::max<size_t>(pipe_chunk, ((size_t)total + stenos_context_s::PIPE_MAX - 1) / stenos_context_s::PIPE_MAX) / sb);
+				const size_t n_chunk = (n_sb + chunk_sb - 1) / chunk_sb;
+				if (n_chunk >= 2 && n_chunk <= (size_t)stenos_context_s::PIPE_MAX && ctx->pipe_offs_reserve(n_sb + 1) && ctx->in.reserve(size + 32) &&
+				    ctx->out.reserve((size_t)total + 32)) {
+					unsigned long long* offs = ctx->pipe_offs;
+					cudaEventRecord(ctx->pipe_ev[0], st); // work already queued on the context's stream (the memset above) comes first
+					cudaStreamWaitEvent(ctx->pipe_in, ctx->pipe_ev[0], 0);
+					size_t at = first, err = 0;
+					for (size_t c = 0; c < n_chunk && !err; ++c) {
+						const size_t lo = c * chunk_sb, hi = std::min(n_sb, lo + chunk_sb);
+						const size_t at0 = at;
+						for (size_t i = lo; i < hi; ++i) { // host_frame_index for this chunk
+							if (at + 4 > size) {
+								err = STENOS_ERROR_SRC_OVERFLOW;
+								break;
+							}
+							offs[i] = at;
+							const size_t csize = (size_t)src[at + 1] | ((size_t)src[at + 2] << 8) | ((size_t)src[at + 3] << 16);
+							if (at + 4 + csize > size) {
+								err = STENOS_ERROR_INVALID_INPUT;
+								break;
+							}
+							at += 4 + csize;
+						}
+						if (err)
+							break;
+						offs[hi] = at;
+						cudaMemcpyAsync(ctx->in.p + at0, src + at0, at - at0, cudaMemcpyHostToDevice, ctx->pipe_in);
+						cudaMemcpyAsync(d_offs + lo, offs + lo, (hi - lo + 1) * 8, cudaMemcpyHostToDevice, ctx->pipe_in);
+						cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->pipe_in);
+						cudaStreamWaitEvent(st, ctx->pipe_ev[2 * c + 1], 0);
+						DecodeParams P;
+						P.ticket = nullptr;
+						P.src = ctx->in.p;
+						P.src_size = at; // everything up to the end of this chunk is on the device
+						P.dst = ctx->out.p;
+						P.total = total;
+						P.sb_bytes = (uint32_t)sb;
+						P.n_sb = (uint32_t)(hi - lo);
+						P.first_sb = (uint32_t)lo;
+						P.sb_offsets = d_offs;
+						P.result = d_result;
+						P.skip_zstd_tail = 0;
+						P.dst_origin = 0;
+						const size_t lr = launch_decode(ctx, T, P);
+						if (is_err(lr)) {
+							err = lr;
+							break;
+						}
+						cudaEventRecord(ctx->pipe_ev[2 * c], st);
+						cudaStreamWaitEvent(ctx->pipe_out, ctx->pipe_ev[2 * c], 0);
+						const size_t o0 = lo * sb, o1 = std::min<uint64_t>((uint64_t)hi * sb, total);
+						cudaMemcpyAsync(dst + o0, ctx->out.p + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->pipe_out);
+					}
+					cudaMemcpyAsync(ctx->host_result, d_result, 16, cudaMemcpyDeviceToHost, st);
+					cudaStreamSynchronize(ctx->pipe_in);
+					const bool ok = cudaStreamSynchronize(st) == cudaSuccess;
+					if (cudaStreamSynchronize(ctx->pipe_out) != cudaSuccess || !ok) {
+						cudaGetLastError();
+						return STENOS_ERROR_UNDEFINED;
+					}
+					if (err)
+						return err;
+					const size_t e = map_device_error(ctx->host_result[1]);
+					if (e)
+						return e;
+					return (size_t)total;
+				}
+			}
+		}
 		if (!src_dev) {
 			unsigned long long* offs = (unsigned long long*)malloc((n_sb + 1) * 8);
 			if (!offs)
@@ -1202,20 +1326,48 @@ size_t stenos_decompress_generic(stenos_context* ctx, const void* src, size_t by
 {
 	return guarded([&]() -> size_t { return decompress_impl(ctx, src, bytesoftype, bytes, dst, dst_size, true, 0); });
 }
+// stenos_compress / stenos_decompress (stenos.cpp:1210-1226) build a context per call in the reference, where that is a
+// few pointer writes.  Here a context owns device scratch, pinned words, streams and events (cudaMalloc, cudaMallocHost and
+// stream creation cost more than a small call's kernels), so every calling thread keeps one and reuses it; the thread's
+// exit releases it.
+namespace
+{
+	struct ThreadContext
+	{
+		stenos_context_s ctx;
+		int dev = -1; // the device its scratch lives on
+		~ThreadContext() { ctx.free_all(); }
+	};
+	stenos_context_s* thread_context()
+	{
+		static thread_local ThreadContext tc;
+		stenos_context_s* c = &tc.ctx;
+		int cur = 0;
+		if (cudaGetDevice(&cur) != cudaSuccess)
+			cudaGetLastError();
+		if (cur != tc.dev) { // the thread switched devices since its last call: the scratch does not follow
+			c->free_all();
+			c->sm_count = 0;
+			tc.dev = cur;
+		}
+		// back to the defaults of a fresh context (stenos.cpp:94-106); the scratch stays
+		c->level = 1;
+		c->threads = 1;
+		c->max_ns = 0;
+		c->custom_shift = STENOS_NO_BLOCK_SHIFT;
+		c->device = -1;
+		return c;
+	}
+}
 size_t stenos_compress(const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size, int level)
 {
-	stenos_context_s ctx;
-	ctx.level = level > 9 ? 9 : (level < 0 ? 0 : level);
-	const size_t r = stenos_compress_generic(&ctx, src, bytesoftype, bytes, dst, dst_size);
-	ctx.free_all();
-	return r;
+	stenos_context_s* ctx = thread_context();
+	ctx->level = level > 9 ? 9 : (level < 0 ? 0 : level);
+	return stenos_compress_generic(ctx, src, bytesoftype, bytes, dst, dst_size);
 }
 size_t stenos_decompress(const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size)
 {
-	stenos_context_s ctx;
-	const size_t r = stenos_decompress_generic(&ctx, src, bytesoftype, bytes, dst, dst_size);
-	ctx.free_all();
-	return r;
+	return stenos_decompress_generic(thread_context(), src, bytesoftype, bytes, dst, dst_size);
 }
 size_t stenos_get_info(const void* src_, size_t bytesoftype, size_t bytes, stenos_info* info)
 {
@@ -1702,6 +1854,23 @@ size_t stenos_b200_synchronize(stenos_context* ctx)
 		return STENOS_ERROR_UNDEFINED;
 	}
 	return 0;
+}
+// Test support: keeps `ctas` SMs busy (one CTA of smem_kb KiB of shared memory each) for about `ns` nanoseconds on the
+// given stream -- the co-residency test launches the encoder next to it.
+size_t stenos_b200_test_occupy(void* cuda_stream, int ctas, unsigned smem_kb, unsigned long long ns)
+{
+#ifndef STENOS_EMU
+	const int smem = (int)smem_kb * 1024;
+	if (cudaFuncSetAttribute((const void*)sb::occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+		cudaGetLastError();
+		return STENOS_ERROR_INVALID_PARAMETER;
+	}
+	sb::occupy_kernel<<<dim3((unsigned)ctas), dim3(32), smem, (cudaStream_t)cuda_stream>>>(ns);
+	return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+#else
+	(void)cuda_stream, (void)ctas, (void)smem_kb, (void)ns;
+	return 0;
+#endif
 }
 unsigned long long stenos_b200_kernel_launches(void)
 {

@@ -20,6 +20,9 @@
 //     warp got slower every turn and the others spun on it, 1.75 ms instead of 0.74 ms.)
 //   * Superblocks come from the global ticket for every CTA, including the first one, so every superblock a
 //     look-back waits for belongs to a CTA that is running (no co-residency assumption).
+//   * A warp never waits in the middle of a task: when its ring is full of pieces whose superblocks are not placed
+//     yet (they may be waiting for this very task), the oldest one moves to a spill slot in HBM and is copied to the
+//     frame from there.  Rare (incompressible data); it is what makes the hand-out of tasks deadlock free.
 //
 // HBM traffic: N read + C written, nothing else.
 #pragma once
@@ -65,20 +68,24 @@ namespace sb
 	constexpr int FLOW_PQ = 8;   // pieces a half-warp may have waiting for their placement
 	constexpr int FLOW_SBQ = 16; // ring of superblock numbers handed to the CTA (> FLOW_NS + 1)
 
-	template<int T, int NT>
+	// T: element size; NT: threads of the encoder warps; KB: blocks per piece.  Pieces and tasks are independent of the
+	// number of warps: NPC pieces (of KB blocks) and NTASK = NPC / 2 tasks per superblock, taken by whichever warp is free.
+	template<int T, int NT, int KB>
 	struct FlowLayout
 	{
 		static constexpr uint32_t BLOCK = T * 256u;
 		static constexpr uint32_t HS = (T + 1) / 2;
 		static constexpr uint32_t MAXB = BLOCK + HS; // worst full block (LZ: 1 + BLOCK)
 		static constexpr uint32_t NW = NT / 32;
-		static constexpr uint32_t NH = 2 * NW; // half-warps = pieces per superblock
+		static constexpr uint32_t NH = 2 * NW; // half-warps
 		static constexpr uint32_t NBLK = DEFAULT_SUPERBLOCK / BLOCK;
-		static constexpr uint32_t KMAX = (NBLK + NH - 1) / NH;
+		static constexpr uint32_t KMAX = KB;
+		static constexpr uint32_t NTASK = (NBLK + 2u * KB - 1u) / (2u * KB); // tasks per superblock
+		static constexpr uint32_t NPC = 2u * NTASK;                          // pieces per superblock
 		static constexpr uint32_t TMP = (BLOCK + HS + 8u * T + 1u + 15u) & ~15u; // worst partial block
 		static constexpr uint32_t HAS_LZ = (T % 4) == 0 ? 1u : 0u;
 		static constexpr uint32_t LZ_STRIDE = (LZ_SCRATCH_BYTES + 15u) & ~15u;
-		static constexpr uint32_t SLOT_BYTES = 64u + NH * 8u;
+		static constexpr uint32_t SLOT_BYTES = 64u + NPC * 8u;
 		static constexpr uint32_t CTL_OFF = 0;                 // sbq[FLOW_SBQ] u64
 		static constexpr uint32_t SLOT_OFF = FLOW_SBQ * 8u;
 		static constexpr uint32_t PINFO_OFF = SLOT_OFF + FLOW_NS * SLOT_BYTES; // [NH][FLOW_PQ] x 16 bytes: pieces waiting for their placement
@@ -97,6 +104,9 @@ namespace sb
 		static constexpr uint32_t REG = ((SMEM_TOTAL - STAGE_OFF - 32u) / NH) & ~15u;
 		static_assert(REG >= REG_MIN, "staging ring too small for this block size / warp count");
 		static constexpr uint32_t smem_bytes() { return STAGE_OFF + NH * REG + 32u; }
+		// HBM spill area (EncodeParams::spill): one slot per half-warp and waiting piece, worst case of a piece each
+		static constexpr uint32_t SPILL_SLOT = (KB * MAXB + 15u) & ~15u;
+		static constexpr size_t spill_bytes(size_t grid) { return grid * NH * (size_t)FLOW_PQ * SPILL_SLOT; }
 	};
 
 	// slot of one superblock in flight (shared memory); sizes / offs follow at +64
@@ -534,6 +544,11 @@ namespace sb
 	// n bytes shared (offset s_off, any alignment) -> global (any alignment), 16-byte stores on the destination's alignment
 	__device__ __forceinline__ void half_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sm, uint32_t s_off, uint32_t n, int r)
 	{
+		if (n <= 16u) { // the pieces of constant regions are a few bytes
+			if ((uint32_t)r < n)
+				dst[r] = sm[s_off + r];
+			return;
+		}
 		const uint32_t head = min((uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u), n);
 		if ((uint32_t)r < head)
 			dst[r] = sm[s_off + r];
@@ -580,16 +595,31 @@ namespace sb
 			dst[done + r] = src[done + r];
 	}
 
+#ifndef STENOS_EMU
+	// test support (stenos_b200_test_occupy): a CTA that holds its SM's shared memory for a while
+	__global__ void occupy_kernel(unsigned long long ns)
+	{
+		extern __shared__ uint8_t occupy_smem[];
+		occupy_smem[threadIdx.x] = 1;
+		unsigned long long t0, t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		do {
+			__nanosleep(2000);
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		} while (t1 - t0 < ns);
+	}
+#endif
+
 	__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 	__device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 	// ------------------------------------------------------------------------------------------
 	// the kernel: NT / 32 encoder warps + 1 placer warp
 	// ------------------------------------------------------------------------------------------
-	template<int T, int NT>
+	template<int T, int NT, int KB>
 	__global__ void __launch_bounds__(NT + 32, 1) encode_flow_kernel(EncodeParams P)
 	{
-		using L = FlowLayout<T, NT>;
+		using L = FlowLayout<T, NT, KB>;
 		STENOS_DYN_SMEM(uint8_t, smem);
 		unsigned long long* sbq = reinterpret_cast<unsigned long long*>(smem + L::CTL_OFF); // (q + 1) << 32 | superblock of the CTA's q-th turn
 		uint32_t* lut = reinterpret_cast<uint32_t*>(smem + L::LUT_OFF);
@@ -599,7 +629,7 @@ namespace sb
 		const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
 		auto slot_of = [&](uint32_t q) { return reinterpret_cast<FlowSlot*>(smem + L::SLOT_OFF + (q % FLOW_NS) * L::SLOT_BYTES); };
 		auto sizes_of = [&](FlowSlot* s) { return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s) + 64); };
-		auto offs_of = [&](FlowSlot* s) { return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s) + 64 + L::NH * 4u); };
+		auto offs_of = [&](FlowSlot* s) { return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s) + 64 + L::NPC * 4u); };
 		// waits decided by lane 0 and broadcast: lanes polling a word on their own may see different values, and what
 		// follows a wait are warp collectives
 		auto wait_u32 = [&](const uint32_t* p, uint32_t want) {
@@ -741,10 +771,13 @@ namespace sb
 		uint32_t* pinfo = reinterpret_cast<uint32_t*>(smem + L::PINFO_OFF) + half * (FLOW_PQ * 4u);
 		uint32_t* pmeta = reinterpret_cast<uint32_t*>(smem + L::PMETA_OFF) + (uint32_t)warp * FLOW_PQ;
 		uint32_t* task_ctr = reinterpret_cast<uint32_t*>(smem + L::TASK_OFF);
-		const uint32_t nblk_sb = P.sb_bytes / L::BLOCK;
-		const uint32_t K = max(1u, (nblk_sb + L::NH - 1u) / L::NH); // blocks per piece
+		constexpr uint32_t K = KB; // blocks per piece
 		uint32_t pq_head = 0, pq_tail = 0;     // my warp's pieces waiting for their placement: entries [pq_head, pq_tail) mod FLOW_PQ
+		uint32_t pq_ring = 0;                  // entries [pq_head, pq_ring) were moved to their spill slots, [pq_ring, pq_tail) sit in the rings
+		uint8_t* const spill = P.spill + ((size_t)blockIdx.x * L::NH + half) * (size_t)FLOW_PQ * L::SPILL_SLOT; // my half's spill slots
 		uint32_t pos = 0, vcur = 0, vtail = 0; // my half's ring: write position, and monotonic counters of bytes claimed / released
+		// bytes of the ring that are used (tests shrink it to the legal minimum so that pieces spill to HBM all the time)
+		const uint32_t REG = P.ring_cap ? min(L::REG, max(L::REG_MIN, P.ring_cap)) : L::REG;
 		const uint32_t stage32 = smem_addr32(smem) + stage;
 		const uint32_t in32 = smem_addr32(smem) + L::IN_OFF + (uint32_t)warp * L::IN_STRIDE; // my warp's input rows (FLOW_STAGING 2)
 		// The row of the block my half encodes NEXT is already on its way from HBM while the current block is encoded
@@ -755,21 +788,38 @@ namespace sb
 			e[i] = 0u;
 		bool have = false;
 
-		auto take_task = [&]() {
+		// A warp takes at most TASK_LIMIT tasks of one turn (its share + 1).  Together with "never wait in the middle of a
+		// task" this is what keeps every wait of this kernel safe: a warp that holds a task only ever waits for a turn OLDER
+		// than the task's, which completes without it (see the waits below).
+#ifndef FLOW_TASK_SLACK
+#define FLOW_TASK_SLACK 1
+#endif
+		constexpr uint32_t TASK_LIMIT = (L::NTASK + L::NW - 1u) / L::NW + FLOW_TASK_SLACK;
+		static_assert(TASK_LIMIT * L::NW >= L::NTASK + L::NW && (uint32_t)FLOW_PQ > TASK_LIMIT, "task limit / waiting list too small");
+		constexpr uint32_t NO_TASK = 0xFFFFFFFFu;
+		uint32_t my_turn = 0xFFFFFFFFu, my_cnt = 0;
+		auto try_take = [&]() -> uint32_t {
+			const uint32_t peek = __shfl_sync(FULL, ld_vol_u32(task_ctr), 0) / L::NTASK;
+			if (peek == my_turn && my_cnt >= TASK_LIMIT)
+				return NO_TASK; // the rest of this turn is for the other warps
 			uint32_t t = 0;
 			if (lane == 0)
 				t = atomicAdd(task_ctr, 1u);
-			return __shfl_sync(FULL, t, 0);
+			t = __shfl_sync(FULL, t, 0);
+			const uint32_t q = t / L::NTASK;
+			my_cnt = q == my_turn ? my_cnt + 1u : 1u;
+			my_turn = q;
+			return t;
 		};
 		// is the oldest waiting piece placed?  (decided by lane 0 for the warp)
 		auto head_ready = [&]() {
-			const uint32_t qo = ld_vol_u32(pmeta + pq_head % FLOW_PQ) / L::NW;
+			const uint32_t qo = ld_vol_u32(pmeta + pq_head % FLOW_PQ) / L::NTASK;
 			return __shfl_sync(FULL, ld_vol_u32(&slot_of(qo)->ready), 0) == qo + 1u;
 		};
 		// copies my half's oldest waiting piece to the frame and releases its ring space (blocks until it is placed)
 		auto drain_one = [&]() {
 			const uint32_t to_ = ld_vol_u32(pmeta + pq_head % FLOW_PQ);
-			const uint32_t qo = to_ / L::NW, jo = to_ % L::NW;
+			const uint32_t qo = to_ / L::NTASK, jo = to_ % L::NTASK;
 			FlowSlot* sl = slot_of(qo);
 			wait_u32(&sl->ready, qo + 1u);
 			__threadfence_block();
@@ -778,11 +828,16 @@ namespace sb
 			const uint32_t pi = 2u * jo + (uint32_t)hb;
 			const uint32_t* pf = pinfo + (pq_head % FLOW_PQ) * 4u;
 			const uint32_t posA = ld_vol_u32(pf + 0), lenA = ld_vol_u32(pf + 1), lenB = ld_vol_u32(pf + 2), vend = ld_vol_u32(pf + 3);
+			const bool spilled = pq_head != pq_ring; // uniform over the warp: both halves' pieces of a task move together
 			if (mode == 0u) {
 				uint8_t* to = P.dst + base + 4u + ld_vol_u32(offs_of(sl) + pi);
-				half_copy_from_smem(to, smem, stage + posA, lenA, r);
-				if (lenB)
-					half_copy_from_smem(to + lenA, smem, stage, lenB, r);
+				if (spilled)
+					half_copy_global(to, spill + (size_t)(pq_head % FLOW_PQ) * L::SPILL_SLOT, lenA + lenB, r);
+				else {
+					half_copy_from_smem(to, smem, stage + posA, lenA, r);
+					if (lenB)
+						half_copy_from_smem(to + lenA, smem, stage, lenB, r);
+				}
 			}
 			else if (mode == 1u) {
 				// COPY superblock (stenos.cpp:609-610): my blocks of the input instead
@@ -794,11 +849,14 @@ namespace sb
 				if (cnt)
 					half_copy_global(P.dst + base + 4u + (uint64_t)b0 * L::BLOCK, P.src + (uint64_t)so * P.sb_bytes + (uint64_t)b0 * L::BLOCK, cnt * L::BLOCK, r);
 			}
-			vtail = vend;
+			if (!spilled) {
+				vtail = vend;
+				pq_ring = pq_head + 1u;
+			}
 			__syncwarp();
 			if (lane == 0) {
 				const uint32_t old = atomicAdd(&sl->consumed, 1u);
-				if (old == L::NW - 1u) {
+				if (old == L::NTASK - 1u) {
 					// every task of this superblock has left: the slot goes to turn qo + FLOW_NS
 					sl->arrived = 0u;
 					sl->consumed = 0u;
@@ -810,30 +868,85 @@ namespace sb
 			++pq_head;
 		};
 
-		uint32_t t = take_task();
+		// moves the oldest piece still in the rings to its spill slot in HBM and releases its ring space
+		auto spill_one = [&]() {
+			const uint32_t* pf = pinfo + (pq_ring % FLOW_PQ) * 4u;
+			const uint32_t posA = ld_vol_u32(pf + 0), lenA = ld_vol_u32(pf + 1), lenB = ld_vol_u32(pf + 2), vend = ld_vol_u32(pf + 3);
+			uint8_t* to = spill + (size_t)(pq_ring % FLOW_PQ) * L::SPILL_SLOT;
+			half_copy_from_smem(to, smem, stage + posA, lenA, r);
+			if (lenB)
+				half_copy_from_smem(to + lenA, smem, stage, lenB, r);
+			vtail = vend;
+			__syncwarp();
+			++pq_ring;
+		};
+		// room for one more block in both rings: the oldest pieces move to their spill slots -- never a wait: the superblock
+		// they belong to may be waiting for the task I am working on.  (Placed pieces leave at the top of every task, so a
+		// ring that fills up in the middle of one holds pieces that are not placed yet.)
+		auto make_room = [&](bool need) {
+			while (__any_sync(FULL, need && vcur + L::MAXB - vtail > REG))
+				spill_one();
+		};
+
+		uint32_t t = try_take();
+		bool finishing = false;
 		for (;;) {
-			const uint32_t q = t / L::NW, j = t % L::NW;
-			// ---- the CTA's q-th superblock
-			unsigned long long tk;
-			while (((tk = __shfl_sync(FULL, *reinterpret_cast<volatile unsigned long long*>(&sbq[q % FLOW_SBQ]), 0)) >> 32) != q + 1u)
-				STENOS_SPIN_HINT();
-			const uint32_t s = (uint32_t)tk;
-			if (s >= P.n_stream)
-				break; // superblocks are handed out in increasing order: this CTA has no further work
-			if (j == L::NW / 2u && lane == 0) {
+			// ---- everything that may wait happens here, at the top of a task, and pieces leave for the frame here only
+			uint32_t q = 0, j = 0, s = 0;
+			FlowSlot* slot = nullptr;
+			bool must_drain = false;
+			for (;;) {
+				if (pq_head != pq_tail && (must_drain || head_ready())) {
+					drain_one(); // (waits for the placement when it must)
+					must_drain = false;
+					continue;
+				}
+				if (finishing) {
+					if (pq_head == pq_tail)
+						break;
+					must_drain = true;
+					continue;
+				}
+				if (t == NO_TASK) {
+					// I hold no task: waiting is safe
+					t = try_take();
+					if (t == NO_TASK)
+						FLOW_LONG_WAIT();
+					continue;
+				}
+				q = t / L::NTASK, j = t % L::NTASK;
+				const unsigned long long tk = __shfl_sync(FULL, *reinterpret_cast<volatile unsigned long long*>(&sbq[q % FLOW_SBQ]), 0);
+				if ((uint32_t)(tk >> 32) != q + 1u) {
+					STENOS_SPIN_HINT(); // the CTA's q-th superblock is being asked for
+					continue;
+				}
+				s = (uint32_t)tk;
+				if (s >= P.n_stream) {
+					// Superblocks are handed out in increasing order: this CTA has no further work.  Warps that already hold a
+					// task of the next turn must see that too (nobody will ask for that turn's superblock any more).
+					if (lane == 0)
+						*reinterpret_cast<volatile unsigned long long*>(&sbq[(q + 1u) % FLOW_SBQ]) = ((unsigned long long)(q + 2u) << 32) | 0xFFFFFFFFull;
+					finishing = true;
+					continue;
+				}
+				if (pq_tail - pq_head >= (uint32_t)FLOW_PQ) {
+					must_drain = true; // no entry left for this piece: the oldest one belongs to an older turn (FLOW_PQ > TASK_LIMIT), safe to wait for
+					continue;
+				}
+				slot = slot_of(q);
+				if (__shfl_sync(FULL, ld_vol_u32(&slot->owner), 0) == q + 1u)
+					break;
+				// the slot is still held by turn q - FLOW_NS: somebody (maybe me) has not copied that superblock out yet
+				FLOW_LONG_WAIT();
+			}
+			if (finishing)
+				break;
+			if (j == L::NTASK / 2u && lane == 0) {
 				// The CTA's next superblock is asked for half a turn ahead: early enough that its number is there when the first
 				// task of the next turn starts, late enough that the ticket does not sit unencoded for long (every superblock
 				// handed out and not yet encoded holds up the placement of all later ones).
 				const uint32_t nx = atomicAdd(P.ticket + 1, 1u);
 				*reinterpret_cast<volatile unsigned long long*>(&sbq[(q + 1u) % FLOW_SBQ]) = ((unsigned long long)(q + 2u) << 32) | nx;
-			}
-			FlowSlot* slot = slot_of(q);
-			while (__shfl_sync(FULL, ld_vol_u32(&slot->owner), 0) != q + 1u) {
-				// the slot is still held by turn q - FLOW_NS: somebody (maybe me) has not copied that superblock out yet
-				if (pq_head != pq_tail && head_ready())
-					drain_one();
-				else
-					FLOW_LONG_WAIT();
 			}
 			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
 			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
@@ -842,40 +955,34 @@ namespace sb
 			const uint32_t b0 = pi * K;
 			const uint32_t cnt = b0 < nfull ? min(K, nfull - b0) : 0u;
 			const uint8_t* blk = in + (uint64_t)b0 * L::BLOCK;
-			while (pq_tail - pq_head >= (uint32_t)FLOW_PQ)
-				drain_one(); // no entry left for this piece
 
 			uint32_t posA = pos, lenA = 0, lenB = 0;
 			bool wrapped = false;
-			uint32_t tnext = 0xFFFFFFFFu; // my warp's next task, taken during the last block of this one
+			uint32_t tnext = NO_TASK; // my warp's next task, taken during the last block of this one
 			const uint32_t kmax = max(1u, __reduce_max_sync(FULL, cnt));
 			for (uint32_t it = 0; it < kmax; ++it) {
 				const bool active = it < cnt;
-				if (active && pos + L::MAXB > L::REG) {
+				if (active && pos + L::MAXB > REG) {
 					// a block never wraps: the piece continues at the start of the ring
-					vcur += L::REG - pos;
+					vcur += REG - pos;
 					pos = 0;
 					wrapped = true;
 				}
-				while (__any_sync(FULL, active && vcur + L::MAXB - vtail > L::REG))
-					drain_one(); // no room: my oldest piece still in the ring has to leave first
-				// pieces that were placed meanwhile leave for the frame
-				while (pq_head != pq_tail && head_ready())
-					drain_one();
+				make_room(active);
 				if (it + 1u == kmax)
-					tnext = take_task();
+					tnext = try_take();
 				const uint8_t* myblk = blk + (size_t)it * L::BLOCK;
 				// my half's next block: the next one of the piece, or the first one of my piece of the next task
 				const uint8_t* nb = nullptr;
 				if (it + 1u < cnt)
 					nb = myblk + L::BLOCK;
-				else if (it + 1u == kmax) {
-					const uint32_t q2 = tnext / L::NW;
+				else if (it + 1u == kmax && tnext != NO_TASK) {
+					const uint32_t q2 = tnext / L::NTASK;
 					const unsigned long long t2 = *reinterpret_cast<volatile unsigned long long*>(&sbq[q2 % FLOW_SBQ]);
 					const uint32_t s2 = (uint32_t)t2;
 					if ((uint32_t)(t2 >> 32) == q2 + 1u && s2 < P.n_stream) {
 						const uint32_t nfull2 = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s2 * P.sb_bytes) / L::BLOCK;
-						const uint32_t b2 = (2u * (tnext % L::NW) + (uint32_t)hb) * K;
+						const uint32_t b2 = (2u * (tnext % L::NTASK) + (uint32_t)hb) * K;
 						if (b2 < nfull2)
 							nb = P.src + (uint64_t)s2 * P.sb_bytes + (uint64_t)b2 * L::BLOCK;
 					}
@@ -941,19 +1048,19 @@ namespace sb
 			if (lane == 0)
 				na = atomicAdd(&slot->arrived, 1u);
 			na = __shfl_sync(FULL, na, 0);
-			if (na == L::NW - 1u) {
+			if (na == L::NTASK - 1u) {
 				// Last task of the superblock: exclusive scan of the piece sizes, and the superblock's size goes out as the
 				// AGGREGATE word of the look-back right away -- successors must never wait for this CTA's placer, which may
 				// itself be waiting for a predecessor (measured: with the placer publishing it, placers spun ~100 % of the time).
 				__threadfence_block();
 				uint32_t* sizes = sizes_of(slot);
 				uint32_t* offs = offs_of(slot);
-				constexpr uint32_t PER = (L::NH + 31u) / 32u;
+				constexpr uint32_t PER = (L::NPC + 31u) / 32u;
 				uint32_t mine[PER], sum = 0;
 #pragma unroll
 				for (uint32_t k = 0; k < PER; ++k) {
 					const uint32_t i = (uint32_t)lane * PER + k;
-					mine[k] = i < L::NH ? ld_vol_u32(sizes + i) : 0u;
+					mine[k] = i < L::NPC ? ld_vol_u32(sizes + i) : 0u;
 					sum += mine[k];
 				}
 				uint32_t incl = sum;
@@ -967,7 +1074,7 @@ namespace sb
 #pragma unroll
 				for (uint32_t k = 0; k < PER; ++k) {
 					const uint32_t i = (uint32_t)lane * PER + k;
-					if (i < L::NH)
+					if (i < L::NPC)
 						st_vol_u32(offs + i, run);
 					run += mine[k];
 				}
@@ -995,8 +1102,6 @@ namespace sb
 			}
 			t = tnext;
 		}
-		while (pq_head != pq_tail)
-			drain_one();
 #if FLOW_STAGING == 2
 		cp_async_wait_all();
 #endif

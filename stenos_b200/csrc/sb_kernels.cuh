@@ -98,7 +98,9 @@ namespace sb
 		unsigned long long* sb_offsets; // optional [n_sb + 1]: offset of every superblock header in dst
 		uint64_t base_offset; // offset in dst of this launch's first superblock when header_len == 0 (multi-GPU segments)
 		uint32_t first_sb;    // encode_frame_kernel: superblocks [first_sb, n_sb) (the ones before were placed by encode_stream_kernel)
-		uint32_t n_stream;    // encode_stream_kernel: superblocks [0, n_stream)
+		uint32_t n_stream;    // encode_stream_kernel / encode_flow_kernel: superblocks [0, n_stream)
+		uint8_t* spill;       // encode_flow_kernel: HBM spill slots (FlowLayout::spill_bytes(grid))
+		uint32_t ring_cap;    // encode_flow_kernel: 0, or (tests) bytes of each staging ring to use
 	};
 
 	constexpr unsigned long long LB_AGGREGATE = 1ull << 62;

@@ -87,3 +87,54 @@ def make(name, count, start=0, seed=0):
     if name == "int32_sorted":
         return np.arange(start, start + count, dtype=np.int64).astype(np.int32)
     raise ValueError("unknown workload %r" % name)
+
+
+# ------------------------------------------------------------------------------------------------
+# The same closed forms evaluated ON THE DEVICE (torch), for shards too large to generate on the host
+# in bench time (config 4: 32 GiB).  Integer generators are bit-identical to the numpy ones; the
+# float-derived ones (sine, sensor) may differ in the last ulp of sin(), i.e. in a handful of
+# elements -- parity checks therefore always read the device's actual input back.
+# ------------------------------------------------------------------------------------------------
+def _s64(c):
+    c &= 0xFFFFFFFFFFFFFFFF
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _lsr_t(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _hash_t(seed, idx):
+    z = (idx ^ _s64(seed)) + _s64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr_t(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr_t(z, 27)) * _s64(0x94D049BB133111EB)
+    return z ^ _lsr_t(z, 31)
+
+
+def make_torch(name, count, start=0, seed=0, device="cuda", chunk=1 << 26):
+    """Device-side twin of make(): returns a torch tensor of `count` elements on `device`."""
+    import torch
+
+    dt = {"int32_ramp_runs": torch.int32, "int64_ramp_runs": torch.int64, "int16_sine": torch.int16, "float64_sensor": torch.float64,
+          "float32_sensor": torch.float32}[name]
+    out = torch.empty(count, dtype=dt, device=device)
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        idx = torch.arange(start + c0, start + c0 + n, dtype=torch.int64, device=device)
+        if name in ("int32_ramp_runs", "int64_ramp_runs"):
+            v = idx * 3 + (_hash_t(seed, idx) & 15) - 8
+            pos = idx & ((1 << 20) - 1)
+            v = torch.where((pos >= 100000) & (pos < 400000), torch.full_like(v, 42), v)
+            out[c0:c0 + n] = v.to(dt)  # int64 -> int32 keeps the low 32 bits (two's complement), like the numpy cast
+        else:
+            h = _hash_t(seed, idx)
+            s = torch.zeros(n, dtype=torch.float64, device=device)
+            for k in range(4):
+                s += (_lsr_t(h, 16 * k) if k else h).bitwise_and(0xFFFF).to(torch.float64)
+            g = (s / 65536.0 - 2.0) * (3.0 ** 0.5)
+            f = idx.to(torch.float64)
+            if name == "int16_sine":
+                out[c0:c0 + n] = torch.round(2000.0 * torch.sin(f / 300.0) + 3.0 * g).to(dt)
+            else:
+                out[c0:c0 + n] = (20.0 + 5.0 * torch.sin(f / 5000.0) + 1e-4 * f + 0.01 * g).to(dt)
+    return out

@@ -260,3 +260,30 @@ def test_split_decoder_matches(monkeypatch):
             bad[i] ^= 0x5A
         r = run(api.decompress, bytes(bad), T, raw.size)  # an error string or bytes, never a crash
         assert isinstance(r, (bytes, str))
+
+
+def test_flow_encoder_spill_path_with_minimum_rings(monkeypatch):
+    """The fast encoder (sb_flow.cuh) with its staging rings at the smallest legal size: pieces whose superblock is not
+    placed yet move to HBM spill slots all the time.  Streams must not change."""
+    monkeypatch.setenv("STENOS_B200_FLOW_RING", "1")
+    for T, name in ((4, "mostly_random_some_repeats"), (8, "lz_then_noise"), (2, "random"), (4, "ramp_noise200")):
+        n = (131072 * 6 + 5000) // T
+        raw = raw_of(dists.make(name, n, T, seed=11))
+        want = port.compress(raw, T)
+        # room beyond stenos_bound: every superblock goes through the fast encoder
+        assert api.Context().compress(raw, T, dst_size=api.bound(raw.size) + 900000) == want, (T, name)
+
+
+def test_pipelined_host_decompress(monkeypatch):
+    """stenos_decompress_generic on host buffers in chunks (H2D, decode, D2H overlapped): small chunks force the path."""
+    monkeypatch.setenv("STENOS_B200_PIPELINE_CHUNK", "262144")
+    for T, name in ((4, "ramp_noise16"), (2, "smooth_sine"), (8, "lz_then_noise"), (4, "random")):
+        for nb in (131072 * 9 + 64 * T, 131072 * 5 + 300 * T + 3, 131072 * 8):
+            raw = raw_of(dists.make(name, nb // T, T, seed=3))
+            c = port.compress(raw, T)
+            assert api.compress(raw, T) == c
+            assert api.decompress(c, T, raw.size) == raw.tobytes(), (T, name, nb)
+    raw = raw_of(dists.make("ramp_noise16", 131072 * 3, 4, seed=1))
+    c = port.compress(raw, 4)
+    for cut in (len(c) - 5, len(c) // 2):
+        assert run(api.decompress, c[:cut], 4, raw.size) == "INVALID_INPUT"

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 150 python tools/bench_rows.py --rows codec > gpurun_out/r2s11_rows_flow.jsonl 2> gpurun_out/r2s11_rows_flow.err
+for v in vW18 vW19 vSlack3; do
+STENOS_B200_LIB=build/variants/$v.so timeout 150 python tools/bench_rows.py --rows codec > gpurun_out/r2s11_rows_$v.jsonl 2> gpurun_out/r2s11_rows_$v.err
+done
+for f in gpurun_out/r2s11_rows_*.jsonl; do echo $f; python - "$f" <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    d=json.loads(l); print("  T=%d compress %.3f ms frac %.3f | decompress %.3f ms frac %.3f parity %s"%(d["T"],d["compress_ms"],d["compress_frac"],d["decompress_ms"],d["decompress_frac"],d.get("parity")))
+PY
+done
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:encode_flow_kernel -c 1 -s 3 -o gpurun_out/r2s11_enc4 -f python tools/time_parts.py > gpurun_out/r2s11_ncu_enc4.log 2>&1

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python tools/bench_rows.py --rows codec > gpurun_out/r2s9_rows_flow.jsonl 2> gpurun_out/r2s9_rows_flow.err
+for v in vW18 vW19; do
+STENOS_B200_LIB=build/variants/$v.so timeout 600 python tools/bench_rows.py --rows codec > gpurun_out/r2s9_rows_$v.jsonl 2> gpurun_out/r2s9_rows_$v.err
+done
+for f in gpurun_out/r2s9_rows_*.jsonl; do echo $f; python - "$f" <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    d=json.loads(l); print("  T=%d compress %.3f ms frac %.3f | decompress %.3f ms frac %.3f"%(d["T"],d["compress_ms"],d["compress_frac"],d["decompress_ms"],d["decompress_frac"]))
+PY
+done
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2s9_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2s9_pytest.log
+tail -3 gpurun_out/r2s9_pytest.log
