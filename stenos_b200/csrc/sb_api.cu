@@ -157,6 +157,19 @@ struct stenos_context_s
 	cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
 	cudaEvent_t pipe_ev[2 * PIPE_MAX] = {};
 	unsigned long long* pipe_host = nullptr; // pinned, 2 words per chunk
+	static constexpr size_t SMALL_BYTES = 65536; // host <-> host calls up to this size return [result][bytes] in one copy
+	uint8_t* small_host = nullptr;               // pinned, 16 + SMALL_BYTES + 64
+	bool small_init()
+	{
+		if (small_host)
+			return true;
+		if (cudaMallocHost((void**)&small_host, 16 + SMALL_BYTES + 64) != cudaSuccess) {
+			cudaGetLastError();
+			small_host = nullptr;
+			return false;
+		}
+		return true;
+	}
 	unsigned long long* pipe_offs = nullptr; // pinned: superblock offsets of a host frame (pipelined decompress)
 	size_t pipe_offs_cap = 0;
 	bool pipe_offs_reserve(size_t n)
@@ -281,6 +294,9 @@ struct stenos_context_s
 		if (pipe_host)
 			cudaFreeHost(pipe_host);
 		pipe_host = nullptr;
+		if (small_host)
+			cudaFreeHost(small_host);
+		small_host = nullptr;
 		if (pipe_offs)
 			cudaFreeHost(pipe_offs);
 		pipe_offs = nullptr;
@@ -872,14 +888,18 @@ namespace
 				dst_direct = true;
 			}
 		}
+		// Small host destinations (a cvector bucket is 1 KiB): [result words][stream] sit next to each other in the device
+		// staging buffer and come back in ONE copy and ONE stream synchronisation instead of two of each.
+		bool small_out = false;
 		if (!dst_direct) {
 			// The staging buffer never needs more than the worst case of the frame (every superblock
 			// stored as COPY); the kernel still receives the caller's dst_size because the reference's
 			// room arithmetic depends on it.
 			const size_t alloc = std::min(dst_size, (size_t)header_len + n_sb * 4 + bytes + 16);
-			if (!ctx->out.reserve(alloc + 16))
+			if (!ctx->out.reserve(alloc + 32))
 				return STENOS_ERROR_ALLOC;
-			d_dst = ctx->out.p;
+			d_dst = ctx->out.p + 16;
+			small_out = !host_tail && dev_bytes != 0 && alloc <= stenos_context_s::SMALL_BYTES && ctx->small_init();
 		}
 
 		size_t total = header_len;
@@ -894,6 +914,27 @@ namespace
 				r = 0;
 			}
 			else {
+				if (small_out) {
+					const size_t alloc = std::min(dst_size, (size_t)header_len + n_sb * 4 + bytes + 16);
+					r = enqueue_encode(ctx, d_src, T, dev_bytes, d_dst, d_cap, sb, header_len, (uint32_t)ctx->shift, bytes, level, reinterpret_cast<unsigned long long*>(ctx->out.p),
+							   nullptr);
+					if (is_err(r))
+						return r;
+					cudaMemcpyAsync(ctx->small_host, ctx->out.p, 16 + alloc, cudaMemcpyDeviceToHost, st);
+					if (cudaStreamSynchronize(st) != cudaSuccess) {
+						cudaGetLastError();
+						return STENOS_ERROR_UNDEFINED;
+					}
+					const unsigned long long* hr = reinterpret_cast<const unsigned long long*>(ctx->small_host);
+					const size_t e = map_device_error(hr[1]);
+					if (e)
+						return e;
+					total = (size_t)hr[0];
+					if (total > dst_size)
+						return STENOS_ERROR_DST_OVERFLOW;
+					memcpy(dst, ctx->small_host + 16, total);
+					return total;
+				}
 				r = enqueue_encode(ctx, d_src, T, dev_bytes, d_dst, d_cap, sb, header_len, (uint32_t)ctx->shift, bytes, level, nullptr, nullptr);
 				if (is_err(r))
 					return r;
@@ -1132,6 +1173,48 @@ namespace
 						return e;
 					return (size_t)total;
 				}
+			}
+		}
+		// ---- small host -> host calls (a cvector bucket is 1 KiB): pinned offsets, [result words][bytes] back in one copy,
+		// one stream synchronisation per call instead of three
+		{
+			const size_t last_dsize0 = (size_t)(total - (uint64_t)(n_sb - 1) * sb);
+			if (!src_dev && !dst_dev && total <= stenos_context_s::SMALL_BYTES && last_dsize0 >= 128 && ctx->small_init() && ctx->pipe_offs_reserve(n_sb + 1) &&
+			    ctx->in.reserve(size + 32) && ctx->out.reserve((size_t)total + 64)) {
+				const size_t e0 = host_frame_index(src, size, first, n_sb, ctx->pipe_offs);
+				if (e0)
+					return e0;
+				const size_t used = (size_t)ctx->pipe_offs[n_sb];
+				unsigned long long* d_res2 = reinterpret_cast<unsigned long long*>(ctx->out.p);
+				cudaMemsetAsync(d_res2, 0, 16, st);
+				cudaMemcpyAsync(ctx->in.p, src, used, cudaMemcpyHostToDevice, st);
+				cudaMemcpyAsync(d_offs, ctx->pipe_offs, (n_sb + 1) * 8, cudaMemcpyHostToDevice, st);
+				DecodeParams P;
+				P.ticket = nullptr;
+				P.src = ctx->in.p;
+				P.src_size = used;
+				P.dst = ctx->out.p + 16;
+				P.total = total;
+				P.sb_bytes = (uint32_t)sb;
+				P.n_sb = (uint32_t)n_sb;
+				P.first_sb = 0;
+				P.sb_offsets = d_offs;
+				P.result = d_res2;
+				P.skip_zstd_tail = 0;
+				P.dst_origin = 0;
+				const size_t lr = launch_decode(ctx, T, P);
+				if (is_err(lr))
+					return lr;
+				cudaMemcpyAsync(ctx->small_host, ctx->out.p, 16 + (size_t)total, cudaMemcpyDeviceToHost, st);
+				if (cudaStreamSynchronize(st) != cudaSuccess) {
+					cudaGetLastError();
+					return STENOS_ERROR_UNDEFINED;
+				}
+				const size_t e = map_device_error(reinterpret_cast<const unsigned long long*>(ctx->small_host)[1]);
+				if (e)
+					return frame ? e : STENOS_ERROR_INVALID_INPUT;
+				memcpy(dst, ctx->small_host + 16, (size_t)total);
+				return (size_t)total;
 			}
 		}
 		if (!src_dev) {

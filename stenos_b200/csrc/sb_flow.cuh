@@ -777,7 +777,10 @@ namespace sb
 		uint8_t* const spill = P.spill + ((size_t)blockIdx.x * L::NH + half) * (size_t)FLOW_PQ * L::SPILL_SLOT; // my half's spill slots
 		uint32_t pos = 0, vcur = 0, vtail = 0; // my half's ring: write position, and monotonic counters of bytes claimed / released
 		// bytes of the ring that are used (tests shrink it to the legal minimum so that pieces spill to HBM all the time)
-		const uint32_t REG = P.ring_cap ? min(L::REG, max(L::REG_MIN, P.ring_cap)) : L::REG;
+		uint32_t REG = P.ring_cap ? min(L::REG, max(L::REG_MIN, P.ring_cap)) : L::REG;
+#ifndef STENOS_EMU
+		asm("" : "+r"(REG)); // one register, not three instructions at every use
+#endif
 		const uint32_t stage32 = smem_addr32(smem) + stage;
 		const uint32_t in32 = smem_addr32(smem) + L::IN_OFF + (uint32_t)warp * L::IN_STRIDE; // my warp's input rows (FLOW_STAGING 2)
 		// The row of the block my half encodes NEXT is already on its way from HBM while the current block is encoded

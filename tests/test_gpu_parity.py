@@ -518,3 +518,33 @@ def test_pipelined_host_decompress_and_cached_contexts():
         cs = api.compress(small, T)
         assert cs == port.compress(small, T)
         assert api.decompress(cs, T, small.size) == small.tobytes()
+
+
+def _ref_program(name):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = os.path.join(root, "oracle", "_ref", name)
+    if not os.path.exists(p):
+        pytest.skip("%s not built (make -C oracle reftests needs /root/reference)" % name)
+    return p
+
+
+def test_reference_own_comp_decomp_test_against_the_boundary():
+    """The reference's tests/tests_comp_decomp.cpp (its test_vector(): sentinels behind dst and behind the decoded buffer,
+    'an error implies dst_size < stenos_bound', round trip, shrinking dst_size) compiled against libstenos_b200.so; the
+    sweep is cut to T in {2, 4, 8} and levels 0..1 (tests/cpp/ref_comp_decomp_cut.cpp)."""
+    import subprocess
+
+    r = subprocess.run([_ref_program("ref_comp_decomp_cut_b200")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "ref_comp_decomp_cut ok" in r.stdout
+
+
+@pytest.mark.skipif(os.environ.get("STENOS_B200_LONG_TESTS") != "1", reason="minutes of per-bucket calls: set STENOS_B200_LONG_TESTS=1")
+def test_reference_own_cvector_test_against_the_boundary():
+    """The reference's tests/test_cvector.cpp, unchanged (cvector<size_t>, <int>, move-only and atomic payloads, 16 reader
+    threads), compiled against libstenos_b200.so."""
+    import subprocess
+
+    r = subprocess.run([_ref_program("ref_test_cvector_main_b200")], capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "ref_test_cvector ok" in r.stdout
