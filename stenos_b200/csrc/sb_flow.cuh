@@ -76,6 +76,9 @@ namespace sb
 		static constexpr uint32_t BLOCK = T * 256u;
 		static constexpr uint32_t HS = (T + 1) / 2;
 		static constexpr uint32_t MAXB = BLOCK + HS; // worst full block (LZ: 1 + BLOCK)
+		// free bytes a half's ring must have at the position of a block: the row stores of flow_store_row run up to
+		// FLOW_STORE_SLACK bytes past the end of what they emit (overwritten by whatever comes next, never read)
+		static constexpr uint32_t ROOM = MAXB + 16u;
 		static constexpr uint32_t NW = NT / 32;
 		static constexpr uint32_t NH = 2 * NW; // half-warps
 		static constexpr uint32_t NBLK = DEFAULT_SUPERBLOCK / BLOCK;
@@ -100,7 +103,7 @@ namespace sb
 		static constexpr uint32_t STAGE_OFF = IN_OFF + NW * IN_STRIDE;
 		static constexpr uint32_t SMEM_TOTAL = 227u * 1024u;
 		// per-half staging ring: a piece (<= KMAX worst blocks) plus the linear tail a block may need before the wrap
-		static constexpr uint32_t REG_MIN = (KMAX + 1u) * MAXB;
+		static constexpr uint32_t REG_MIN = (KMAX + 1u) * ROOM;
 		static constexpr uint32_t REG = ((SMEM_TOTAL - STAGE_OFF - 32u) / NH) & ~15u;
 		static_assert(REG >= REG_MIN, "staging ring too small for this block size / warp count");
 		static constexpr uint32_t smem_bytes() { return STAGE_OFF + NH * REG + 32u; }
@@ -136,9 +139,11 @@ namespace sb
 #ifdef STENOS_EMU
 	__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)(reinterpret_cast<const uint8_t*>(p) - emu::st().dyn_smem); }
 	__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { emu::st().dyn_smem[a] = (uint8_t)v; }
+	__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { emu::st().dyn_smem[a] = (uint8_t)v, emu::st().dyn_smem[a + 1] = (uint8_t)(v >> 8); }
 #else
 	__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 	__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+	__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; st.shared.b16 [%0], lo; }" ::"r"(a), "r"(v)); }
 #endif
 
 #ifdef STENOS_EMU
@@ -194,13 +199,50 @@ namespace sb
 	// row payload helpers
 	// ------------------------------------------------------------------------------------------
 
-	// stores the first n (0..16) bytes of w[0..3] at the shared-window address at
-	__device__ __forceinline__ void flow_store16(uint32_t at, const uint32_t (&w)[4], uint32_t n)
+	// Stores the n bytes (0, or 2..16: no row payload is one byte long) of a row, w[0..3], at the shared-window address
+	// `at` -- WITHOUT a predicate per byte (16 compares + 16 predicated byte stores + 12 shifts per row before).  A row
+	// with n != 0 always stores 16 (17 when `at` is odd) bytes: eight aligned halfwords in DESCENDING address order, then
+	// its first byte.  What runs past the row's n bytes lands on bytes that are written later: the rows after it (they
+	// start >= 2 bytes further on, so their halfword of the same step is a different one, and the halfword that holds
+	// valid data for a clobbered address belongs to an earlier step index = a LATER instruction; a row's first byte,
+	// which an odd-aligned predecessor's last halfword may touch, goes last of all), the next plane, the next block
+	// (FlowLayout::ROOM keeps that many bytes free).  Shared-memory stores of one warp are performed in program order.
+	__device__ __forceinline__ void flow_store_row(uint32_t at, const uint32_t (&w)[4], uint32_t n)
 	{
-#pragma unroll
-		for (uint32_t j = 0; j < 16; ++j)
-			if (j < n)
-				sts_u8(at + j, w[j >> 2] >> (8 * (j & 3)));
+		const uint32_t odd = at & 1u, s = odd * 8u, R = at + odd;
+		const uint32_t v0 = __funnelshift_r(w[0], w[1], s), v1 = __funnelshift_r(w[1], w[2], s), v2 = __funnelshift_r(w[2], w[3], s), v3 = w[3] >> s;
+#ifdef STENOS_EMU
+		// the emulator runs the lanes of a warp one after the other between two collectives: a rendez-vous after every
+		// store gives the stores the order they have on the GPU (called by all 32 lanes)
+#define FLOW_ROW_STEP(stmt) \
+	do { \
+		if (n != 0u) \
+			stmt; \
+		__syncwarp(); \
+	} while (0)
+		FLOW_ROW_STEP(sts_u16(R + 14u, v3 >> 16));
+		FLOW_ROW_STEP(sts_u16(R + 12u, v3));
+		FLOW_ROW_STEP(sts_u16(R + 10u, v2 >> 16));
+		FLOW_ROW_STEP(sts_u16(R + 8u, v2));
+		FLOW_ROW_STEP(sts_u16(R + 6u, v1 >> 16));
+		FLOW_ROW_STEP(sts_u16(R + 4u, v1));
+		FLOW_ROW_STEP(sts_u16(R + 2u, v0 >> 16));
+		FLOW_ROW_STEP(sts_u16(R, v0));
+		FLOW_ROW_STEP(sts_u8(at, w[0]));
+#undef FLOW_ROW_STEP
+#else
+		if (n != 0u) {
+			sts_u16(R + 14u, v3 >> 16);
+			sts_u16(R + 12u, v3);
+			sts_u16(R + 10u, v2 >> 16);
+			sts_u16(R + 8u, v2);
+			sts_u16(R + 6u, v1 >> 16);
+			sts_u16(R + 4u, v1);
+			sts_u16(R + 2u, v0 >> 16);
+			sts_u16(R, v0);
+			sts_u8(at, w[0]);
+		}
+#endif
 	}
 
 	// (lo,hi) << (8 * nbytes) as a 128-bit value OR-ed into w[0..3]; nbytes in 0..10, the value has at most 8 bytes
@@ -287,27 +329,35 @@ namespace sb
 		uint32_t sz = (hent >> 9) & 31u;
 		uint32_t h = hent & 15u;
 		uint32_t pay = (hent >> 4) & 31u;
-		uint32_t x[4], nzd[4], nzx[4];
-		delta_repeats(d, x);
-		uint32_t nr = 0, nd = 0;
+		// RLE on the values and on the deltas (:439-474).  Neither can win over a packed row of size <= 3: rs = 2 + (bytes
+		// that differ from their predecessor) < 3 means a constant row that continues the previous byte, whose size is 1,
+		// and the same holds for the deltas -- planes of constant rows and single steps (the upper bytes of a counter)
+		// skip the counting for the whole warp.
+		uint32_t nzd[4] = { 0u, 0u, 0u, 0u }, nzx[4] = { 0u, 0u, 0u, 0u };
+		bool use_rle = false, use_drle = false;
+		if (__any_sync(FULL, sz > 3u)) {
+			uint32_t x[4];
+			delta_repeats(d, x);
+			uint32_t nr = 0, nd = 0;
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			nzd[j] = nonzero_bytes(d[j]);
-			nzx[j] = nonzero_bytes(x[j]);
-			nr = sad4_acc(nzd[j], 0u, nr);
-			nd = sad4_acc(nzx[j], 0u, nd);
-		}
-		const uint32_t rs = (nr >> 7) + 2u, ds = (nd >> 7) + 2u; // :439-474
-		const bool use_rle = rs < sz;
-		sz = min(sz, rs);
-		const bool use_drle = ds < sz;
-		if (use_drle) {
-			h = 6u;
-			pay = ds;
-		}
-		else if (use_rle) {
-			h = 7u;
-			pay = rs;
+			for (int j = 0; j < 4; ++j) {
+				nzd[j] = nonzero_bytes(d[j]);
+				nzx[j] = nonzero_bytes(x[j]);
+				nr = sad4_acc(nzd[j], 0u, nr);
+				nd = sad4_acc(nzx[j], 0u, nd);
+			}
+			const uint32_t rs = (nr >> 7) + 2u, ds = (nd >> 7) + 2u;
+			use_rle = rs < sz;
+			sz = min(sz, rs);
+			use_drle = ds < sz;
+			if (use_drle) {
+				h = 6u;
+				pay = ds;
+			}
+			else if (use_rle) {
+				h = 7u;
+				pay = rs;
+			}
 		}
 		const bool needmin = !(use_rle || use_drle || h == 15u);
 
@@ -341,14 +391,15 @@ namespace sb
 		kind_out = kind;
 
 		// ---- emission (:739-806)
+		uint32_t w[4] = { a[0], a[1], a[2], a[3] };
+		uint32_t rowp = o + 16u * (uint32_t)r, n = 0u;
 		if (emit) {
 			if (kind == KIND_SAME) {
 				if (r == 0)
 					sts_u8(o, a[0]);
 			}
 			else {
-				uint32_t w[4] = { a[0], a[1], a[2], a[3] };
-				uint32_t rowp = o + 16u * (uint32_t)r, n = 16u;
+				n = 16u;
 				if (kind != KIND_RAW) {
 					if (r & 1) // row headers: two nibbles per byte, row 2i in the low nibble
 						sts_u8(o + ((uint32_t)r >> 1), (hmp & 0xFu) | (h << 4));
@@ -378,9 +429,9 @@ namespace sb
 						flow_pack_row(v, h & 7u, w);
 					}
 				}
-				flow_store16(rowp, w, n);
 			}
 		}
+		flow_store_row(rowp, w, n); // all 32 lanes, n = 0: nothing to store
 		return total;
 	}
 
@@ -459,6 +510,22 @@ namespace sb
 			asm("" : "+r"(X[g])); // keeps X in its register (the compiler recomputed the 16-LOP3 chain for every plane instead)
 #endif
 		row_consumed(); // every word of the row has been read (XA depends on all of them): the input buffer may be refilled
+
+		// both blocks of the warp are one value each (runs): [kinds = 0][T plane bytes], nothing to analyse
+		bool all_same = XA[0] == 0u;
+		if constexpr (NG == 2)
+			all_same = all_same && XA[1] == 0u;
+		if (all_same) {
+			if (active && r == 0) {
+#pragma unroll
+				for (uint32_t i = 0; i < HS; ++i)
+					sts_u8(out32 + i, 0u);
+#pragma unroll
+				for (uint32_t p = 0; p < (uint32_t)T; ++p)
+					sts_u8(out32 + HS + p, F[p >> 2] >> (8u * (p & 3u)));
+			}
+			return active ? HS + (uint32_t)T : 0u;
+		}
 
 		uint32_t pos = HS, kinds = 0;
 #pragma unroll
@@ -887,7 +954,7 @@ namespace sb
 		// they belong to may be waiting for the task I am working on.  (Placed pieces leave at the top of every task, so a
 		// ring that fills up in the middle of one holds pieces that are not placed yet.)
 		auto make_room = [&](bool need) {
-			while (__any_sync(FULL, need && vcur + L::MAXB - vtail > REG))
+			while (__any_sync(FULL, need && vcur + L::ROOM - vtail > REG))
 				spill_one();
 		};
 
@@ -965,7 +1032,7 @@ namespace sb
 			const uint32_t kmax = max(1u, __reduce_max_sync(FULL, cnt));
 			for (uint32_t it = 0; it < kmax; ++it) {
 				const bool active = it < cnt;
-				if (active && pos + L::MAXB > REG) {
+				if (active && pos + L::ROOM > REG) {
 					// a block never wraps: the piece continues at the start of the ring
 					vcur += REG - pos;
 					pos = 0;
