@@ -648,8 +648,7 @@ namespace
 		ctx->index_ran = true;
 		STENOS_LAUNCH(index_scan_kernel, dim3((unsigned)((n_seg + INDEX_WARPS - 1) / INDEX_WARPS)), dim3(INDEX_WARPS * 32), 0, st, F);
 		STENOS_LAUNCH(index_merge_kernel, dim3(1), dim3(1024), 256, st, F);
-		STENOS_LAUNCH(index_fill_kernel, dim3((unsigned)((n_seg + 127) / 128)), dim3(128), 0, st, F);
-		g_launches += 3;
+		g_launches += 2;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 
@@ -1866,6 +1865,12 @@ namespace
 					if (fused_chunks) {
 						FilterParams F = P;
 						F.bytes = fused_chunks * chunk;
+						if (T == 8 && fused_chunks <= 65535 && ctx->scan.reserve(fused_chunks * 16)) {
+							// the even planes' byte sums first (the odd planes continue their quarter streams), at memory rate
+							F.plane_totals = reinterpret_cast<const uint32_t*>(ctx->scan.p);
+							STENOS_LAUNCH(plane_totals_kernel, dim3(4, (unsigned)fused_chunks), dim3(PLANE_TOTALS_THREADS), PLANE_TOTALS_THREADS / 32 * 4, st, F);
+							++g_launches;
+						}
 						switch (T) {
 							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
 							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;

@@ -259,11 +259,22 @@ namespace sb
 		w[3] |= k == 0u ? 0u : (k == 1u ? t2 : t1);
 	}
 
+	// hides from the compiler that x is a power of two: x * y + z stays ONE IMAD (fma pipe) instead of SHF + IADD on
+	// the alu pipe, which is the busy one in this kernel
+	__device__ __forceinline__ uint32_t flow_opaque(uint32_t x)
+	{
+#ifndef STENOS_EMU
+		asm("" : "+r"(x));
+#endif
+		return x;
+	}
+
 	// bit packing of 16 values (< 2^bits, one per byte of v[0..3]) LSB first: 2 * bits bytes in w (:540-602; two groups
-	// of 8 values of `bits` bytes each are one contiguous string of 16 * bits bits)
+	// of 8 values of `bits` bytes each are one contiguous string of 16 * bits bits).  bits in 1..7.  Every shift by a
+	// variable amount is a multiplication by a power of two (IMAD / IMAD.WIDE).
 	__device__ __forceinline__ void flow_pack_row(const uint32_t (&v)[4], uint32_t bits, uint32_t (&w)[4])
 	{
-		const uint32_t mul = 1u << bits, mul2 = mul * mul;
+		const uint32_t mul = flow_opaque(1u << bits), mul2 = flow_opaque(mul * mul), mul4 = flow_opaque(mul2 * mul2);
 		uint32_t pk[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
@@ -271,15 +282,19 @@ namespace sb
 			const uint32_t c = __byte_perm(v[j], 0u, 0x4341) * mul + __byte_perm(v[j], 0u, 0x4240);
 			pk[j] = __byte_perm(c, 0u, 0x4432) * mul2 + __byte_perm(c, 0u, 0x4410);
 		}
-		const uint32_t p0 = pk[0], p1 = pk[1], p2 = pk[2], p3 = pk[3];
-		const uint32_t s = 4u * bits; // 4..24
-		const uint32_t g0l = p0 | (p1 << s), g0h = p1 >> (32u - s);
-		const uint32_t g1l = p2 | (p3 << s), g1h = p3 >> (32u - s);
-		w[0] = g0l;
-		w[1] = g0h;
-		w[2] = 0u;
-		w[3] = 0u;
-		flow_or_shifted(w, g1l, g1h, bits);
+		// a group of 8 values = 8 * bits bits: pk[odd] << 4 * bits on top of pk[even]
+		const unsigned long long g0 = (unsigned long long)pk[1] * mul4 + pk[0];
+		const unsigned long long g1 = (unsigned long long)pk[3] * mul4 + pk[2];
+		// group 1 follows group 0 at byte `bits`: g1 << 8 * (bits & 3), placed at word bits >> 2 (0 or 1)
+		const uint32_t mb = flow_opaque(1u << ((bits & 3u) * 8u));
+		const unsigned long long t = (unsigned long long)(uint32_t)g1 * mb;
+		const unsigned long long u = (unsigned long long)(uint32_t)(g1 >> 32) * mb + (uint32_t)(t >> 32);
+		const uint32_t t0 = (uint32_t)t, t1 = (uint32_t)u, t2 = (uint32_t)(u >> 32);
+		const bool k0 = bits < 4u;
+		w[0] = (uint32_t)g0 | (k0 ? t0 : 0u);
+		w[1] = (uint32_t)(g0 >> 32) | (k0 ? t1 : t0);
+		w[2] = k0 ? t2 : t1;
+		w[3] = k0 ? 0u : t2;
 	}
 
 	// RLE row payload [mask:2][bytes of src whose mask bit is clear] (:258-293).  nz[j]: 0x80 in every byte of the

@@ -451,6 +451,10 @@ namespace sb
 	}
 
 	constexpr int INDEX_WARPS = 4;
+#ifndef INDEX_SPAN_BYTES
+#define INDEX_SPAN_BYTES 16 // measured: 64 bytes per lane (all loads of a round in flight) is slower, 0.151 vs 0.092 ms per GiB of int32: more candidates per lane serialise the chain checks
+#endif
+	constexpr int INDEX_SPAN = INDEX_SPAN_BYTES; // bytes a lane scans per round (multiple of 16)
 
 	__global__ void __launch_bounds__(INDEX_WARPS * 32) index_scan_kernel(FastIndexParams P)
 	{
@@ -466,22 +470,28 @@ namespace sb
 		else {
 			// a true header lies within one superblock (4 + max_csize bytes) of any position inside the chain
 			const uint64_t scan_end = min(P.src_size, (uint64_t)(lo + 4ull + P.max_csize));
-			for (uint64_t x0 = lo; x0 < scan_end; x0 += 32 * 16) {
-				// lane scans 16 consecutive positions; candidates first by their code byte (SWAR), then the chain
-				const uint64_t xb = x0 + 16ull * lane;
+			// A lane scans INDEX_SPAN consecutive positions per round (the warp: 32 * INDEX_SPAN bytes); all loads of a
+			// round are issued before the first use -- the scan is a chain of memory latencies, one per round.
+			const uint32_t hi_max = P.max_csize >> 16;
+			const uint32_t kadd = hi_max < 0x7Fu ? (0x7Fu - hi_max) * 0x01010101u : 0u;
+			for (uint64_t x0 = lo; x0 < scan_end; x0 += 32 * INDEX_SPAN) {
+				const uint64_t xb = x0 + (uint64_t)INDEX_SPAN * lane;
 				unsigned long long found = IDX_NONE;
-				uint32_t cand = 0;
-				uint32_t w[5] = { 0u, 0u, 0u, 0u, 0u };
+				uint32_t w[INDEX_SPAN / 4 + 1];
+#pragma unroll
+				for (int j = 0; j <= INDEX_SPAN / 4; ++j)
+					w[j] = 0u;
 				if (xb < scan_end) {
 					const uint8_t* p = P.src + xb;
-					if (xb + 16 <= P.src_size && (((uintptr_t)p) & 3u) == 0) {
+					if (xb + INDEX_SPAN <= P.src_size && (((uintptr_t)p) & 15u) == 0) {
 #pragma unroll
-						for (int j = 0; j < 4; ++j)
-							w[j] = reinterpret_cast<const uint32_t*>(p)[j];
+						for (int j = 0; j < INDEX_SPAN / 16; ++j) {
+							const uint4 v = reinterpret_cast<const uint4*>(p)[j];
+							w[4 * j] = v.x, w[4 * j + 1] = v.y, w[4 * j + 2] = v.z, w[4 * j + 3] = v.w;
+						}
 					}
 					else {
-#pragma unroll
-						for (int j = 0; j < 4; ++j) {
+						for (int j = 0; j < INDEX_SPAN / 4; ++j) {
 							uint32_t v = 0;
 #pragma unroll
 							for (int b = 0; b < 4; ++b)
@@ -490,34 +500,38 @@ namespace sb
 						}
 					}
 				}
-				// A header's csize is at most max_csize, so its top byte (3 bytes after the code) is small: a second SWAR
-				// filter on the bytes already loaded (the next lane holds the 3 bytes past mine) removes nearly all of the
-				// code-byte look-alikes before the chain check, which costs dependent loads.
-				w[4] = __shfl_down_sync(FULL, w[0], 1);
+				// Candidates first by their code byte (SWAR).  A header's csize is at most max_csize, so its top byte (3
+				// bytes after the code) is small: a second SWAR filter on the bytes already loaded (the next lane holds the
+				// 3 bytes past mine) removes nearly all of the code-byte look-alikes before the chain check, which costs
+				// dependent loads.
+				w[INDEX_SPAN / 4] = __shfl_down_sync(FULL, w[0], 1);
 				if (lane == 31)
-					w[4] = 0u; // unknown: lets the last three positions pass
+					w[INDEX_SPAN / 4] = 0u; // unknown: lets the last three positions pass
 				if (xb < scan_end) {
-					const uint32_t hi_max = P.max_csize >> 16;
-					const uint32_t kadd = hi_max < 0x7Fu ? (0x7Fu - hi_max) * 0x01010101u : 0u;
 #pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						uint32_t z = zero_bytes(w[j] ^ 0x01010101u) | zero_bytes(w[j] ^ 0x06060606u) | zero_bytes(w[j] ^ 0x02020202u);
-						if (hi_max < 0x7Fu) {
-							const uint32_t t3 = __funnelshift_r(w[j], w[j + 1], 24); // byte b + 3 at position b
-							z &= ~(((t3 & 0x7F7F7F7Fu) + kadd) | t3);
+					for (int g = 0; g < INDEX_SPAN / 16 && found == IDX_NONE; ++g) {
+						uint32_t cand = 0;
+#pragma unroll
+						for (int j = 0; j < 4; ++j) {
+							const uint32_t wj = w[4 * g + j];
+							uint32_t z = zero_bytes(wj ^ 0x01010101u) | zero_bytes(wj ^ 0x06060606u) | zero_bytes(wj ^ 0x02020202u);
+							if (hi_max < 0x7Fu) {
+								const uint32_t t3 = __funnelshift_r(wj, w[4 * g + j + 1], 24); // byte b + 3 at position b
+								z &= ~(((t3 & 0x7F7F7F7Fu) + kadd) | t3);
+							}
+							cand |= flags_to_mask4(z) << (4 * j);
 						}
-						cand |= flags_to_mask4(z) << (4 * j);
-					}
-				}
-				while (cand) {
-					const uint32_t b = (uint32_t)__ffs((int)cand) - 1u;
-					cand &= cand - 1u;
-					const uint64_t x = xb + b;
-					if (x >= scan_end)
-						break;
-					if (index_chain_plausible(P.src, P.src_size, x, P.max_csize)) {
-						found = x;
-						break;
+						while (cand) {
+							const uint32_t b = (uint32_t)__ffs((int)cand) - 1u;
+							cand &= cand - 1u;
+							const uint64_t x = xb + 16u * g + b;
+							if (x >= scan_end)
+								break;
+							if (index_chain_plausible(P.src, P.src_size, x, P.max_csize)) {
+								found = x;
+								break;
+							}
+						}
 					}
 				}
 				const uint32_t m = __ballot_sync(FULL, found != IDX_NONE);
@@ -638,6 +652,19 @@ namespace sb
 		__syncthreads();
 		if (tid == 0)
 			*P.ok = sm[0];
+		if (sm[0]) {
+			// accepted: every segment's headers are walked again (L2 hits) and written at the segment's base -- here, not
+			// in a third launch (index_fill_kernel: 14 us for a frame of 8192 superblocks, most of it the launch)
+			for (uint32_t k = tid; k < P.n_seg; k += blockDim.x) {
+				const uint32_t cnt = P.seg_count[k];
+				uint32_t at_i = P.seg_base[k];
+				unsigned long long pos = P.seg_start[k];
+				for (uint32_t i = 0; i < cnt && at_i < P.n_sb; ++i, ++at_i) {
+					P.sb_offsets[at_i] = pos;
+					pos = index_next(P.src, P.src_size, pos);
+				}
+			}
+		}
 		if (!sm[0] && tid == 0) {
 			// fallback: the serial walk (stenos.cpp:1124-1143)
 			uint64_t at = P.first;
@@ -654,21 +681,6 @@ namespace sb
 			P.sb_offsets[P.n_sb] = at;
 			if (at > P.src_size)
 				atomicOr(&P.result[1], (unsigned long long)DEV_ERR_INVALID_INPUT);
-		}
-	}
-
-	// accepted: every segment walks its headers again (L2 hits) and writes them at its base
-	__global__ void __launch_bounds__(128) index_fill_kernel(FastIndexParams P)
-	{
-		const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-		if (k >= P.n_seg || *P.ok == 0u)
-			return;
-		const uint32_t cnt = P.seg_count[k];
-		uint32_t at_i = P.seg_base[k];
-		unsigned long long pos = P.seg_start[k];
-		for (uint32_t i = 0; i < cnt && at_i < P.n_sb; ++i, ++at_i) {
-			P.sb_offsets[at_i] = pos;
-			pos = index_next(P.src, P.src_size, pos);
 		}
 	}
 
