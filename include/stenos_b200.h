@@ -158,6 +158,19 @@ STENOS_B200_EXPORT size_t stenos_b200_gather_decode_async(stenos_context* ctx, c
 							 size_t decompressed_bytes, const unsigned long long* d_sb_offsets, size_t n_buckets_total,
 							 const unsigned int* d_bucket_ids, size_t n, void* d_dst, unsigned long long* d_result);
 
+/* stenos::cvector, the write side (cvector.hpp:1394-1420): compresses n buckets of a device
+ * resident array in ONE launch.  Bucket i is bytes [id * bucket_bytes, (id + 1) * bucket_bytes) of d_src (id =
+ * d_bucket_ids[i], or i when d_bucket_ids is NULL; the array's last bucket may be shorter) and is written as a bare
+ * superblock [code][csize:3][payload] at d_slots + i * slot_stride -- byte for byte what
+ * stenos_private_compress_block(ctx, bucket, bytesoftype, bucket_bytes, bytes, slot, slot_stride) returns, including the
+ * decisions that depend on the room (cvector passes slot_stride = bucket_bytes + 16).
+ * d_sizes[i] = 4 + csize (0 and error bit 1 in d_result[1] when the slot is too small).  bucket_bytes: a multiple of
+ * 256 elements, at most 128 KiB.  The slots + sizes are what stenos_b200_gather_decode_async reads through an offset
+ * index (offset i = i * slot_stride). */
+STENOS_B200_EXPORT size_t stenos_b200_compress_buckets_async(stenos_context* ctx, const void* d_src, size_t bytesoftype, size_t bucket_bytes, size_t total_bytes,
+							    const unsigned int* d_bucket_ids, size_t n, void* d_slots, size_t slot_stride, unsigned int* d_sizes,
+							    unsigned long long* d_result);
+
 /* Waits for the context's stream. */
 STENOS_B200_EXPORT size_t stenos_b200_synchronize(stenos_context* ctx);
 /* Test support: keeps `ctas` SMs busy (one CTA holding smem_kb KiB of shared memory each) for about `ns` nanoseconds

@@ -169,6 +169,11 @@ class Context:
         """1: the last parallel frame index was accepted, 0: it fell back to the serial walk, -1: none ran."""
         return int(self._lib.stenos_b200_index_accepted(self._h))
 
+    def compress_buckets_async(self, d_src, bytesoftype, bucket_bytes, total_bytes, d_ids, n, d_slots, slot_stride, d_sizes, d_result):
+        """n cvector buckets in one launch (cvector.hpp:1394-1420): bare superblocks in fixed slots + their sizes."""
+        return check(self._lib.stenos_b200_compress_buckets_async(self._h, ptr_of(d_src), bytesoftype, bucket_bytes, total_bytes, ptr_of(d_ids), n, ptr_of(d_slots), slot_stride,
+                                                                   ptr_of(d_sizes), ptr_of(d_result)), "stenos_b200_compress_buckets_async")
+
     def gather_decode_async(self, d_frame, frame_bytes, bytesoftype, bucket_bytes, out_bytes, d_sb_offsets, n_buckets, d_ids, n, d_dst, d_result):
         return check(self._lib.stenos_b200_gather_decode_async(self._h, ptr_of(d_frame), frame_bytes, bytesoftype, bucket_bytes, out_bytes, ptr_of(d_sb_offsets), n_buckets,
                                                                 ptr_of(d_ids), n, ptr_of(d_dst), ptr_of(d_result)), "stenos_b200_gather_decode_async")

@@ -5,7 +5,19 @@
 // (header layout, superblock sizing, error codes) follows stenos.cpp line by line (cited inline);
 // all data-path work runs on the GPU.  The only host-side data work is the Zstd coding of a final
 // superblock shorter than 128 bytes (stenos.cpp:435-437), which the reference delegates to libzstd
-// as well -- here through dlopen("libzstd.so.1").
+// as well -- here through dlopen("libzstd.so.1").  Frames written at level >= 2 are decoded by the hybrid path at the
+// end of this file: host Zstd, device filters and block decoder (decompress_hybrid).
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <thread>
+#include <vector>
+#include <dlfcn.h>
+
 #include "sb_kernels.cuh"
 #include "sb_stream.cuh"
 #include "sb_flow.cuh"
@@ -14,13 +26,6 @@
 #include "sb_filters.cuh"
 #include "../../include/stenos_b200.h"
 
-#include <atomic>
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <dlfcn.h>
 
 namespace
 {
@@ -145,7 +150,7 @@ struct stenos_context_s
 	size_t superblock = 0;
 	int shift = 0;
 	// scratch
-	DevBuf in, out, ctl, idx, scan, dtk, blk, spill;
+	DevBuf in, out, ctl, idx, scan, dtk, blk, spill, hyb, hoffs;
 	bool serial_index = false; // tests: force the serial header walk
 	bool legacy_encoder = false; // tests: every superblock through encode_frame_kernel
 	bool legacy_decoder = false;
@@ -288,6 +293,8 @@ struct stenos_context_s
 		dtk.release();
 		blk.release();
 		spill.release();
+		hyb.release();
+		hoffs.release();
 		if (host_result)
 			cudaFreeHost(host_result);
 		host_result = nullptr;
@@ -358,6 +365,39 @@ namespace
 		const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb - P.first_sb, ctx->sm_count));
 		auto kern = encode_frame_kernel<T, NT>;
 		STENOS_LAUNCH(kern, dim3(grid), dim3(NT), smem, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
+	// bucket mode of encode_frame_kernel (EncodeParams::bucket_stride): buckets of one 256-element block run as small
+	// CTAs (one warp, slots for one block: 8 CTAs per SM and more), larger buckets with the frame layout
+	template<int T>
+	size_t launch_buckets_T(stenos_context* ctx, const EncodeParams& P)
+	{
+		const bool one_block = P.sb_bytes <= (uint32_t)T * 256u;
+		if (one_block) {
+			const uint32_t smem = EncodeLayout<T, 1>::smem_bytes(1);
+			int per_sm = 8;
+#ifndef STENOS_EMU
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_frame_kernel<T, 32, 1>, 32, smem) != cudaSuccess || per_sm < 1) {
+				cudaGetLastError();
+				per_sm = 8;
+			}
+#endif
+			const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, (long long)ctx->sm_count * per_sm));
+			auto kern = encode_frame_kernel<T, 32, 1>;
+			STENOS_LAUNCH(kern, dim3(grid), dim3(32), smem, ctx->stream(), P);
+		}
+		else {
+			constexpr int NT = 256;
+			const uint32_t smem = EncodeLayout<T>::smem_bytes(NT / 32);
+			if (cudaFuncSetAttribute((const void*)encode_frame_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_ALLOC;
+			}
+			const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, ctx->sm_count));
+			auto kern = encode_frame_kernel<T, NT>;
+			STENOS_LAUNCH(kern, dim3(grid), dim3(NT), smem, ctx->stream(), P);
+		}
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
@@ -648,7 +688,8 @@ namespace
 		ctx->index_ran = true;
 		STENOS_LAUNCH(index_scan_kernel, dim3((unsigned)((n_seg + INDEX_WARPS - 1) / INDEX_WARPS)), dim3(INDEX_WARPS * 32), 0, st, F);
 		STENOS_LAUNCH(index_merge_kernel, dim3(1), dim3(1024), 256, st, F);
-		g_launches += 2;
+		STENOS_LAUNCH(index_fill_kernel, dim3((unsigned)((n_seg + 127) / 128)), dim3(128), 0, st, F);
+		g_launches += 3;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
 
@@ -1018,7 +1059,9 @@ namespace
 		return 0;
 	}
 
-	size_t decompress_impl(stenos_context* ctx, const void* src_, size_t T, size_t size, void* dst_, size_t dst_size, bool frame, size_t bare_sb)
+	size_t decompress_hybrid(stenos_context* ctx, const uint8_t* src, bool src_dev, size_t T, size_t size, uint8_t* dst, size_t dst_size, size_t prior_error);
+
+	size_t decompress_level1(stenos_context* ctx, const void* src_, size_t T, size_t size, void* dst_, size_t dst_size, bool frame, size_t bare_sb)
 	{
 		if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
 			return STENOS_ERROR_INVALID_BYTESOFTYPE; // stenos.cpp:1067-1068
@@ -1317,6 +1360,41 @@ namespace
 			}
 		}
 		return (size_t)total;
+	}
+
+	// stenos_decompress_generic / stenos_private_decompress_block.  Frames written by the reference at level >= 2 hold
+	// superblocks that went through Zstd (codes 2..5, stenos.cpp:34-39): those take the hybrid path below (host Zstd,
+	// device filters / block decoder).  The first superblock's code is looked at up front; a frame that starts with
+	// level-1 superblocks and has Zstd ones further on comes back from the device decoder as invalid input and is
+	// then looked at again by the hybrid path (which returns that error if it finds no Zstd superblock either).
+	size_t decompress_impl(stenos_context* ctx, const void* src_, size_t T, size_t size, void* dst_, size_t dst_size, bool frame, size_t bare_sb)
+	{
+		if (!frame || !supported_T(T) || size < 13)
+			return decompress_level1(ctx, src_, T, size, dst_, dst_size, frame, bare_sb);
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		const uint8_t* src = static_cast<const uint8_t*>(src_);
+		const bool src_dev = is_device_ptr(src);
+		uint8_t h[16] = { 0 };
+		const size_t hl = std::min<size_t>(size, 16);
+		if (src_dev) {
+			cudaMemcpyAsync(h, src, hl, cudaMemcpyDeviceToHost, ctx->stream());
+			cudaStreamSynchronize(ctx->stream());
+		}
+		else
+			memcpy(h, src, hl);
+		const size_t first = h[0] == 255 ? 12 : 8;
+		const unsigned code0 = first < hl ? h[first] : 0u;
+		uint64_t total = 0;
+		for (int i = 0; i < 7; ++i)
+			total |= (uint64_t)h[1 + i] << (8 * i);
+		// (a code-2 superblock of a level-1 frame is its tail of < 128 bytes: decompress_level1 handles it)
+		if (code0 == 3u || code0 == 4u || code0 == 5u || (code0 == (unsigned)CODE_ZSTD && total >= 128))
+			return decompress_hybrid(ctx, src, src_dev, T, size, static_cast<uint8_t*>(dst_), dst_size, 0);
+		const size_t r = decompress_level1(ctx, src_, T, size, dst_, dst_size, frame, bare_sb);
+		if (r == STENOS_ERROR_INVALID_INPUT)
+			return decompress_hybrid(ctx, src, src_dev, T, size, static_cast<uint8_t*>(dst_), dst_size, r);
+		return r;
 	}
 
 	template<class F>
@@ -1770,6 +1848,61 @@ size_t stenos_b200_gather_decode_async(stenos_context* ctx, const void* d_frame,
 	});
 }
 
+size_t stenos_b200_compress_buckets_async(stenos_context* ctx, const void* d_src, size_t T, size_t bucket_bytes, size_t total_bytes, const unsigned int* d_bucket_ids,
+					  size_t n, void* d_slots, size_t slot_stride, unsigned int* d_sizes, unsigned long long* d_result)
+{
+	return guarded([&]() -> size_t {
+		size_t r = check_async_args(ctx, T, const_cast<void*>(d_src));
+		if (r)
+			return r;
+		if (ctx->level > 1 || ctx->max_ns != 0)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		if (!d_slots || !d_sizes || !d_result || bucket_bytes == 0 || bucket_bytes % (T * 256) != 0 || bucket_bytes > STENOS_BLOCK_SIZE || slot_stride < 8 ||
+		    slot_stride > 0xFFFFFFF0ull || n > 0xFFFFFFF0ull)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		// a last bucket shorter than 128 bytes is Zstd's on the host (stenos.cpp:435-437): use stenos_private_compress_block for it
+		const size_t tail = total_bytes % bucket_bytes;
+		if (tail != 0 && tail < 128)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		cudaStream_t st = ctx->stream();
+		cudaMemsetAsync(d_result, 0, 16, st);
+		if (!n)
+			return 0;
+		if (!ctx->dtk.reserve(64))
+			return STENOS_ERROR_ALLOC;
+		cudaMemsetAsync(ctx->dtk.p, 0, 64, st);
+		EncodeParams P;
+		P.src = (const uint8_t*)d_src;
+		P.bytes = total_bytes;
+		P.dst = (uint8_t*)d_slots;
+		P.dst_size = (uint64_t)n * slot_stride;
+		P.sb_bytes = (uint32_t)bucket_bytes;
+		P.n_sb = (uint32_t)n;
+		P.header_len = 0;
+		P.shift_byte = 255;
+		P.frame_bytes = total_bytes;
+		P.level = ctx->level;
+		P.state = nullptr;
+		P.ticket = reinterpret_cast<uint32_t*>(ctx->dtk.p);
+		P.result = d_result;
+		P.sb_offsets = nullptr;
+		P.base_offset = 0;
+		P.first_sb = 0;
+		P.n_stream = 0;
+		P.spill = nullptr;
+		P.ring_cap = 0;
+		P.bucket_stride = (uint32_t)slot_stride;
+		P.bucket_ids = d_bucket_ids;
+		P.bucket_sizes = d_sizes;
+		switch (T) {
+			case 2: return launch_buckets_T<2>(ctx, P);
+			case 4: return launch_buckets_T<4>(ctx, P);
+			case 8: return launch_buckets_T<8>(ctx, P);
+		}
+		return STENOS_ERROR_INVALID_PARAMETER;
+	});
+}
+
 } // extern "C"
 
 // ---- filters --------------------------------------------------------------------------------
@@ -1865,12 +1998,6 @@ namespace
 					if (fused_chunks) {
 						FilterParams F = P;
 						F.bytes = fused_chunks * chunk;
-						if (T == 8 && fused_chunks <= 65535 && ctx->scan.reserve(fused_chunks * 16)) {
-							// the even planes' byte sums first (the odd planes continue their quarter streams), at memory rate
-							F.plane_totals = reinterpret_cast<const uint32_t*>(ctx->scan.p);
-							STENOS_LAUNCH(plane_totals_kernel, dim3(4, (unsigned)fused_chunks), dim3(PLANE_TOTALS_THREADS), PLANE_TOTALS_THREADS / 32 * 4, st, F);
-							++g_launches;
-						}
 						switch (T) {
 							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
 							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
@@ -1911,6 +2038,226 @@ namespace
 			}
 		}
 		return cudaGetLastError() == cudaSuccess ? bytes : STENOS_ERROR_UNDEFINED;
+	}
+
+	// ------------------------------------------------------------------------------------------
+	// Hybrid decoder of frames written at level >= 2 (decompress_generic_superblock, stenos.cpp:681-753).  Zstd runs on
+	// the host (the reference links it too; here libzstd.so.1 through dlopen), everything else on the device:
+	//   code 2  Zstd(raw)                         -> host Zstd, stored as a COPY superblock
+	//   code 3  Zstd(shuffle(raw))                -> host Zstd, COPY superblock, then unshuffle_kernel over the superblock
+	//   code 4  Zstd(delta(shuffle(raw)))         -> host Zstd, COPY superblock, then unshuffle_delta_kernel
+	//   code 5  Zstd(block stream)                -> host Zstd, stored as a code-1 superblock for decode_pairs_kernel
+	//   code 1 / 6                                -> as they are
+	// The "lowered" superblocks sit in fixed slots of 4 + superblock bytes (the device decoder takes any offsets), so the
+	// host threads (stenos_set_threads) work on independent superblocks.  One H2D copy, one decode launch, one filter
+	// launch per run of code-3 / code-4 superblocks, chunk = the frame's superblock size.
+	// ------------------------------------------------------------------------------------------
+	size_t decompress_hybrid(stenos_context* ctx, const uint8_t* src, bool src_dev, size_t T, size_t size, uint8_t* dst, size_t dst_size, size_t prior_error)
+	{
+		cudaStream_t st = ctx->stream();
+		const bool dst_dev = is_device_ptr(dst);
+		std::unique_ptr<uint8_t[]> host_frame;
+		if (src_dev) {
+			host_frame.reset(new (std::nothrow) uint8_t[size]);
+			if (!host_frame)
+				return STENOS_ERROR_ALLOC;
+			cudaMemcpyAsync(host_frame.get(), src, size, cudaMemcpyDeviceToHost, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+			src = host_frame.get();
+		}
+		// ---- frame header (stenos.cpp:1078-1107)
+		if (size < 8)
+			return STENOS_ERROR_SRC_OVERFLOW;
+		const unsigned shift = src[0];
+		if (shift > 4 && shift != 255)
+			return STENOS_ERROR_INVALID_INPUT;
+		uint64_t total = 0;
+		for (int i = 0; i < 7; ++i)
+			total |= (uint64_t)src[1 + i] << (8 * i);
+		if (total > dst_size)
+			return STENOS_ERROR_DST_OVERFLOW;
+		if (total == 0)
+			return 0;
+		size_t first = 8, sb;
+		if (shift == 255) {
+			if (size < 12)
+				return STENOS_ERROR_SRC_OVERFLOW;
+			sb = (size_t)src[8] | ((size_t)src[9] << 8) | ((size_t)src[10] << 16) | ((size_t)src[11] << 24);
+			first = 12;
+			if (sb == 0)
+				return STENOS_ERROR_INVALID_INPUT;
+		}
+		else
+			sb = default_superblock(T) << shift;
+		const size_t n_sb = (size_t)((total + sb - 1) / sb);
+		if (n_sb > 0xFFFFFFF0ull || sb > 0xFFFFFFu)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		// ---- the walk (stenos.cpp:1124-1143)
+		std::vector<unsigned long long> at(n_sb + 1);
+		bool any = false;
+		{
+			size_t a = first;
+			for (size_t i = 0; i < n_sb; ++i) {
+				if (a + 4 > size)
+					return STENOS_ERROR_SRC_OVERFLOW;
+				at[i] = a;
+				const unsigned code = src[a];
+				any = any || (code >= 2u && code <= 5u);
+				const size_t csize = (size_t)src[a + 1] | ((size_t)src[a + 2] << 8) | ((size_t)src[a + 3] << 16);
+				if (a + 4 + csize > size)
+					return STENOS_ERROR_INVALID_INPUT;
+				a += 4 + csize;
+			}
+			at[n_sb] = a;
+		}
+		if (!any)
+			return prior_error ? prior_error : STENOS_ERROR_INVALID_INPUT; // a level-1 frame: decompress_level1's verdict stands
+		if (!load_zstd())
+			return STENOS_ERROR_ZSTD_INTERNAL;
+		// ---- lower every superblock into its slot
+		const size_t slot = (4 + sb + 15) & ~(size_t)15;
+		const size_t lowered = n_sb * slot;
+		std::unique_ptr<uint8_t[]> low(new (std::nothrow) uint8_t[lowered + 32]);
+		std::vector<uint8_t> filt(n_sb, 0);
+		if (!low)
+			return STENOS_ERROR_ALLOC;
+		std::atomic<size_t> next(0);
+		std::atomic<size_t> failed(0);
+		auto work = [&]() {
+			for (;;) {
+				const size_t i = next.fetch_add(1);
+				if (i >= n_sb || failed.load())
+					return;
+				const size_t dsize = (size_t)std::min<uint64_t>(sb, total - (uint64_t)i * sb);
+				const uint8_t* p = src + at[i];
+				const unsigned code = p[0];
+				const size_t csize = (size_t)(at[i + 1] - at[i]) - 4;
+				uint8_t* o = low.get() + i * slot;
+				size_t len = 0;
+				unsigned out_code = CODE_COPY;
+				if (code == (unsigned)CODE_BLOCK || code == (unsigned)CODE_COPY) {
+					if (csize > sb || (code == (unsigned)CODE_COPY && csize != dsize)) {
+						failed.store(STENOS_ERROR_INVALID_INPUT);
+						return;
+					}
+					memcpy(o + 4, p + 4, csize);
+					len = csize;
+					out_code = code;
+				}
+				else if (code >= 2u && code <= 5u) {
+					const size_t cap = code == 5u ? sb : dsize; // :734: the block stream may be as long as a superblock
+					const size_t zr = p_zstd_decompress(o + 4, cap, p + 4, csize);
+					if (p_zstd_iserror(zr) || ((code == 3u || code == 4u) && zr != dsize)) {
+						failed.store(STENOS_ERROR_INVALID_INPUT);
+						return;
+					}
+					if (code == 5u) {
+						len = zr;
+						out_code = CODE_BLOCK;
+						if (zr == 0) {
+							failed.store(STENOS_ERROR_INVALID_INPUT);
+							return;
+						}
+					}
+					else {
+						if (zr < dsize)
+							memset(o + 4 + zr, 0, dsize - zr); // code 2 (:697-699 only checks for a Zstd error)
+						len = dsize;
+						filt[i] = code == 3u ? 1 : (code == 4u ? 2 : 0);
+					}
+				}
+				else {
+					failed.store(STENOS_ERROR_INVALID_INPUT); // :746-748
+					return;
+				}
+				o[0] = (uint8_t)out_code;
+				o[1] = (uint8_t)len;
+				o[2] = (uint8_t)(len >> 8);
+				o[3] = (uint8_t)(len >> 16);
+			}
+		};
+		{
+			const size_t nt = std::min<size_t>(std::max(1, ctx->threads), std::min<size_t>(n_sb, 256));
+			std::vector<std::thread> pool;
+			for (size_t t = 1; t < nt; ++t)
+				pool.emplace_back(work);
+			work();
+			for (auto& t : pool)
+				t.join();
+		}
+		if (failed.load())
+			return failed.load();
+		std::vector<unsigned long long> loffs(n_sb + 1);
+		for (size_t i = 0; i <= n_sb; ++i)
+			loffs[i] = (unsigned long long)(i * slot);
+		// ---- device: copy, decode, inverse filters
+		if (!ctx->in.reserve(lowered + 32) || !ctx->hoffs.reserve((n_sb + 1) * 8) || !ctx->ctl.reserve(64) || !ctx->out.reserve((size_t)total + 32))
+			return STENOS_ERROR_ALLOC;
+		unsigned long long* d_offs = reinterpret_cast<unsigned long long*>(ctx->hoffs.p);
+		unsigned long long* d_result = reinterpret_cast<unsigned long long*>(ctx->ctl.p);
+		cudaMemsetAsync(d_result, 0, 16, st);
+		cudaMemcpyAsync(ctx->in.p, low.get(), lowered, cudaMemcpyHostToDevice, st);
+		cudaMemcpyAsync(d_offs, loffs.data(), (n_sb + 1) * 8, cudaMemcpyHostToDevice, st);
+		cudaStreamSynchronize(st); // pageable sources
+		DecodeParams P;
+		P.ticket = nullptr;
+		P.src = ctx->in.p;
+		P.src_size = lowered;
+		P.dst = ctx->out.p;
+		P.total = total;
+		P.sb_bytes = (uint32_t)sb;
+		P.n_sb = (uint32_t)n_sb;
+		P.first_sb = 0;
+		P.sb_offsets = d_offs;
+		P.result = d_result;
+		P.skip_zstd_tail = 0;
+		P.dst_origin = 0;
+		const size_t lr = launch_decode(ctx, T, P);
+		if (is_err(lr))
+			return lr;
+		bool any_filter = false;
+		for (size_t i = 0; i < n_sb; ++i)
+			any_filter = any_filter || filt[i] != 0;
+		if (any_filter && !ctx->hyb.reserve((size_t)total + 32))
+			return STENOS_ERROR_ALLOC;
+		for (size_t i = 0; i < n_sb;) {
+			size_t j = i + 1;
+			while (j < n_sb && filt[j] == filt[i])
+				++j;
+			if (filt[i]) {
+				const size_t off = i * sb;
+				const size_t bytes = (size_t)std::min<uint64_t>(total, (uint64_t)j * sb) - off;
+				const size_t fr = filter_impl(ctx, OP_UNSHUFFLE, T, bytes, sb, ctx->out.p + off, ctx->hyb.p + off, filt[i] == 2 ? 1 : 0);
+				if (is_err(fr))
+					return fr;
+			}
+			i = j;
+		}
+		cudaMemcpyAsync(ctx->host_result, d_result, 16, cudaMemcpyDeviceToHost, st);
+		if (cudaStreamSynchronize(st) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_UNDEFINED;
+		}
+		const size_t e = map_device_error(ctx->host_result[1]);
+		if (e)
+			return e;
+		for (size_t i = 0; i < n_sb;) {
+			size_t j = i + 1;
+			while (j < n_sb && (filt[j] != 0) == (filt[i] != 0))
+				++j;
+			const size_t off = i * sb;
+			const size_t bytes = (size_t)std::min<uint64_t>(total, (uint64_t)j * sb) - off;
+			cudaMemcpyAsync(dst + off, (filt[i] ? ctx->hyb.p : ctx->out.p) + off, bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+			i = j;
+		}
+		if (cudaStreamSynchronize(st) != cudaSuccess) {
+			cudaGetLastError();
+			return STENOS_ERROR_UNDEFINED;
+		}
+		return (size_t)total;
 	}
 }
 

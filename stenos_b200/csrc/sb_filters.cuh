@@ -25,7 +25,6 @@ namespace sb
 		uint64_t chunk; // bytes per independently filtered piece (last one may be shorter)
 		uint32_t with_delta; // shuffle: also apply the byte delta (fused); unshuffle: unused
 		uint32_t chunk_in_y; // grid layout of the transposes: 0: x = chunk, y = groups of a chunk; 1: the other way round
-		const uint32_t* plane_totals = nullptr; // unshuffle_delta_kernel<8>: byte sums of the even planes, [chunk][4] (plane_totals_kernel)
 	};
 
 	// position i of a chunk of `bytes` bytes starts a delta stream? (delta.cpp:42-70)
@@ -397,43 +396,6 @@ namespace sb
 	// is an affine map last = a * prev + c with a = 0 if it holds a restart, and the CTA scans maps, two planes per
 	// register (compose_maps2).  Requires cb % (16 * T) == 0 and 16-byte aligned chunks (the host checks).
 	// ------------------------------------------------------------------------------------------
-	// byte sums (mod 256 taken by the reader) of plane `2 * blockIdx.x` of chunk blockIdx.y, for unshuffle_delta_kernel<8>:
-	// every thread keeps PLANE_TOTALS_UNROLL 16-byte loads in flight, one CTA per plane
-	constexpr int PLANE_TOTALS_THREADS = 256;
-	__global__ void __launch_bounds__(PLANE_TOTALS_THREADS) plane_totals_kernel(FilterParams P)
-	{
-		STENOS_DYN_SMEM(uint32_t, ws); // [PLANE_TOTALS_THREADS / 32]
-		const uint64_t c = blockIdx.y;
-		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
-		const uint64_t n = cb / 8;
-		const uint8_t* src = P.src + c * P.chunk + (uint64_t)(2 * blockIdx.x) * n;
-		const uint64_t nv = n / 16; // n is a multiple of 16 (the host checks)
-		const uint4* v = reinterpret_cast<const uint4*>(src);
-		uint32_t s = 0;
-		uint64_t j = threadIdx.x;
-		for (; j + 3ull * PLANE_TOTALS_THREADS < nv; j += 4ull * PLANE_TOTALS_THREADS) {
-			const uint4 a = v[j], b = v[j + PLANE_TOTALS_THREADS], d = v[j + 2 * PLANE_TOTALS_THREADS], e = v[j + 3 * PLANE_TOTALS_THREADS];
-			s = sad4_acc(a.x, 0u, sad4_acc(a.y, 0u, sad4_acc(a.z, 0u, sad4_acc(a.w, 0u, s))));
-			s = sad4_acc(b.x, 0u, sad4_acc(b.y, 0u, sad4_acc(b.z, 0u, sad4_acc(b.w, 0u, s))));
-			s = sad4_acc(d.x, 0u, sad4_acc(d.y, 0u, sad4_acc(d.z, 0u, sad4_acc(d.w, 0u, s))));
-			s = sad4_acc(e.x, 0u, sad4_acc(e.y, 0u, sad4_acc(e.z, 0u, sad4_acc(e.w, 0u, s))));
-		}
-		for (; j < nv; j += PLANE_TOTALS_THREADS) {
-			const uint4 a = v[j];
-			s = sad4_acc(a.x, 0u, sad4_acc(a.y, 0u, sad4_acc(a.z, 0u, sad4_acc(a.w, 0u, s))));
-		}
-		s = __reduce_add_sync(FULL, s);
-		if ((threadIdx.x & 31) == 0)
-			ws[threadIdx.x >> 5] = s;
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			uint32_t t = 0;
-			for (int i = 0; i < PLANE_TOTALS_THREADS / 32; ++i)
-				t += ws[i];
-			const_cast<uint32_t*>(P.plane_totals)[c * 4 + blockIdx.x] = t;
-		}
-	}
-
 #ifndef UNSHUFFLE_DELTA_NT
 #define UNSHUFFLE_DELTA_NT 128 // measured: 128 > 256 > 512 > 1024 threads (more CTAs per SM, cheaper barriers)
 #endif
@@ -457,15 +419,9 @@ namespace sb
 #pragma unroll
 		for (int pp = 0; pp < NP; ++pp)
 			run[pp] = 0u;
-		if (T == 8 && P.plane_totals) {
-			// n = q / 2: an odd plane starts in the middle of a quarter stream, on top of the sum of the plane before it,
-			// which plane_totals_kernel computed at full memory rate (0.5 N of extra reads)
-#pragma unroll
-			for (int e = 0; e < NP; ++e)
-				run[e] = (P.plane_totals[c * NP + e] & 0xFFu) << 16; // planes 2e (starts a stream: 0) and 2e + 1
-		}
-		else if (T == 8) {
-			// the same sums inside this CTA (callers without the scratch array): one extra read of the even planes
+		if (T == 8) {
+			// n = q / 2: an odd plane starts in the middle of a quarter stream, on top of the sum of the plane before it.
+			// One extra read of the even planes (they are read again below, from L2).
 			uint32_t s[NP];
 #pragma unroll
 			for (int e = 0; e < NP; ++e)

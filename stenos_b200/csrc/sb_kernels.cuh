@@ -101,20 +101,27 @@ namespace sb
 		uint32_t n_stream;    // encode_stream_kernel / encode_flow_kernel: superblocks [0, n_stream)
 		uint8_t* spill;       // encode_flow_kernel: HBM spill slots (FlowLayout::spill_bytes(grid))
 		uint32_t ring_cap;    // encode_flow_kernel: 0, or (tests) bytes of each staging ring to use
+		// encode_frame_kernel in BUCKET mode (stenos_b200_compress_buckets_async, cvector.hpp:1394-1420): superblock s is
+		// the bare, independent superblock of bucket ids[s] (or s) written at dst + s * bucket_stride with
+		// dst_size = bucket_stride, as one stenos_private_compress_block call per bucket would; no chain, no frame header
+		uint32_t bucket_stride = 0;            // 0: frame mode
+		const uint32_t* bucket_ids = nullptr;  // optional [n_sb]
+		uint32_t* bucket_sizes = nullptr;      // [n_sb]: 4 + csize, or 0 when the slot is too small
 	};
 
 	constexpr unsigned long long LB_AGGREGATE = 1ull << 62;
 	constexpr unsigned long long LB_INCLUSIVE = 2ull << 62;
 	constexpr unsigned long long LB_VALUE = (1ull << 62) - 1;
 
-	template<int T>
+	// MB: most full blocks of a superblock (the shared-memory slots are sized for it)
+	template<int T, uint32_t MB = DEFAULT_SUPERBLOCK / (T * 256u)>
 	struct EncodeLayout
 	{
 		static constexpr uint32_t BLOCK = T * 256u;
 		static constexpr uint32_t HS = (T + 1) / 2;
 		// worst full block BLOCK + HS (LZ: 1 + BLOCK); worst partial block 1 + HS + 8 * T + (BLOCK - 1); 16-byte aligned
 		static constexpr uint32_t STRIDE = (BLOCK + HS + 8u * T + 1u + 15u) & ~15u;
-		static constexpr uint32_t MAX_BLOCKS = DEFAULT_SUPERBLOCK / BLOCK;
+		static constexpr uint32_t MAX_BLOCKS = MB;
 		static constexpr uint32_t SLOTS_BYTES = MAX_BLOCKS * STRIDE;
 		static constexpr uint32_t NENT = MAX_BLOCKS + 1; // + partial
 		// [slots][sizes u32 x NENT][offsets u32 x (NENT+1)][misc 16 x u64][lz scratch per warp]
@@ -133,10 +140,11 @@ namespace sb
 		return nfull * (T * 256u + (T + 1) / 2) + (rem ? 1u + (T + 1) / 2 + 8u * T + rem : 0u);
 	}
 
-	template<int T, int NT>
-	__global__ void __launch_bounds__(NT, 1) encode_frame_kernel(EncodeParams P)
+	template<int T, int NT, uint32_t MB = DEFAULT_SUPERBLOCK / (T * 256u)>
+	__global__ void __launch_bounds__(NT, MB == DEFAULT_SUPERBLOCK / (T * 256u) ? 1 : 8) encode_frame_kernel(EncodeParams P)
 	{
-		using L = EncodeLayout<T>;
+		using L = EncodeLayout<T, MB>;
+		const bool buckets = P.bucket_stride != 0u;
 		STENOS_DYN_SMEM(uint8_t, smem);
 		uint32_t* sizes = reinterpret_cast<uint32_t*>(smem + L::SIZES_OFF);
 		uint32_t* offs = reinterpret_cast<uint32_t*>(smem + L::OFFS_OFF);
@@ -161,19 +169,26 @@ namespace sb
 				break;
 			if (tid == 0)
 				next_ticket = P.first_sb + atomicAdd(P.ticket, 1u);
-			const uint8_t* in = P.src + (uint64_t)s * P.sb_bytes;
-			const uint32_t in_bytes = (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - (uint64_t)s * P.sb_bytes);
+			const uint64_t in_at = (uint64_t)((buckets && P.bucket_ids) ? P.bucket_ids[s] : s) * P.sb_bytes;
+			const uint8_t* in = P.src + in_at;
+			const uint32_t in_bytes = in_at < P.bytes ? (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - in_at) : 0u;
 			const uint32_t nfull = in_bytes / L::BLOCK, rem = in_bytes - nfull * L::BLOCK;
 			const uint32_t nent = nfull + (rem ? 1u : 0u);
 
 			// ---- can the reference's dst room checks change anything for this superblock?
 			// lower bound of the room: every earlier superblock stored as COPY
 			const uint32_t need = worst_stream<T>(nfull, rem) + 8u * T + 32u;
-			const long long room_lb = (long long)P.dst_size - (long long)(first_off + (uint64_t)s * (4ull + P.sb_bytes)) - 4;
+			const long long room_lb = buckets ? (long long)P.bucket_stride - 4 : (long long)P.dst_size - (long long)(first_off + (uint64_t)s * (4ull + P.sb_bytes)) - 4;
 			bool have_base = false, exact = false;
 			uint64_t base = 0; // offset of this superblock's header in dst
 			long long room = room_lb;
-			if (P.level != 0 && room_lb < (long long)need) {
+			if (buckets) {
+				// the bucket's slot is its whole dst (stenos.cpp:768-778): base and room are known, nothing to wait for
+				base = (uint64_t)s * P.bucket_stride;
+				have_base = true;
+				exact = P.level != 0 && room < (long long)need;
+			}
+			else if (P.level != 0 && room_lb < (long long)need) {
 				// wait for the true offset first
 				if (tid == 0) {
 					uint64_t excl = 0;
@@ -295,7 +310,9 @@ namespace sb
 						top -= 32;
 					}
 				}
-				if (lane == 0) {
+				if (lane == 0 && buckets)
+					misc[1] = base;
+				else if (lane == 0) {
 					st_volatile_u64(&P.state[s], LB_INCLUSIVE | (unsigned long long)(excl + out_size));
 					misc[1] = first_off + excl;
 					if (P.sb_offsets) {
@@ -309,12 +326,17 @@ namespace sb
 			}
 			__syncthreads();
 			base = misc[1];
-			if (base + out_size > P.dst_size) {
+			if (buckets ? (out_size > P.bucket_stride || in_bytes == 0u) : (base + out_size > P.dst_size)) {
 				// stenos.cpp:366-367 / :611-612: the caller's buffer is too small
-				if (tid == 0)
+				if (tid == 0) {
 					atomicOr(&P.result[1], (unsigned long long)DEV_ERR_DST_OVERFLOW);
+					if (buckets)
+						P.bucket_sizes[s] = 0u;
+				}
 				continue;
 			}
+			if (buckets && tid == 0)
+				P.bucket_sizes[s] = out_size;
 
 			// ---- copy out: [code][csize:3] + payload
 			uint8_t* out = P.dst + base;
@@ -451,10 +473,6 @@ namespace sb
 	}
 
 	constexpr int INDEX_WARPS = 4;
-#ifndef INDEX_SPAN_BYTES
-#define INDEX_SPAN_BYTES 16 // measured: 64 bytes per lane (all loads of a round in flight) is slower, 0.151 vs 0.092 ms per GiB of int32: more candidates per lane serialise the chain checks
-#endif
-	constexpr int INDEX_SPAN = INDEX_SPAN_BYTES; // bytes a lane scans per round (multiple of 16)
 
 	__global__ void __launch_bounds__(INDEX_WARPS * 32) index_scan_kernel(FastIndexParams P)
 	{
@@ -470,28 +488,22 @@ namespace sb
 		else {
 			// a true header lies within one superblock (4 + max_csize bytes) of any position inside the chain
 			const uint64_t scan_end = min(P.src_size, (uint64_t)(lo + 4ull + P.max_csize));
-			// A lane scans INDEX_SPAN consecutive positions per round (the warp: 32 * INDEX_SPAN bytes); all loads of a
-			// round are issued before the first use -- the scan is a chain of memory latencies, one per round.
-			const uint32_t hi_max = P.max_csize >> 16;
-			const uint32_t kadd = hi_max < 0x7Fu ? (0x7Fu - hi_max) * 0x01010101u : 0u;
-			for (uint64_t x0 = lo; x0 < scan_end; x0 += 32 * INDEX_SPAN) {
-				const uint64_t xb = x0 + (uint64_t)INDEX_SPAN * lane;
+			for (uint64_t x0 = lo; x0 < scan_end; x0 += 32 * 16) {
+				// lane scans 16 consecutive positions; candidates first by their code byte (SWAR), then the chain
+				const uint64_t xb = x0 + 16ull * lane;
 				unsigned long long found = IDX_NONE;
-				uint32_t w[INDEX_SPAN / 4 + 1];
-#pragma unroll
-				for (int j = 0; j <= INDEX_SPAN / 4; ++j)
-					w[j] = 0u;
+				uint32_t cand = 0;
+				uint32_t w[5] = { 0u, 0u, 0u, 0u, 0u };
 				if (xb < scan_end) {
 					const uint8_t* p = P.src + xb;
-					if (xb + INDEX_SPAN <= P.src_size && (((uintptr_t)p) & 15u) == 0) {
+					if (xb + 16 <= P.src_size && (((uintptr_t)p) & 3u) == 0) {
 #pragma unroll
-						for (int j = 0; j < INDEX_SPAN / 16; ++j) {
-							const uint4 v = reinterpret_cast<const uint4*>(p)[j];
-							w[4 * j] = v.x, w[4 * j + 1] = v.y, w[4 * j + 2] = v.z, w[4 * j + 3] = v.w;
-						}
+						for (int j = 0; j < 4; ++j)
+							w[j] = reinterpret_cast<const uint32_t*>(p)[j];
 					}
 					else {
-						for (int j = 0; j < INDEX_SPAN / 4; ++j) {
+#pragma unroll
+						for (int j = 0; j < 4; ++j) {
 							uint32_t v = 0;
 #pragma unroll
 							for (int b = 0; b < 4; ++b)
@@ -500,38 +512,34 @@ namespace sb
 						}
 					}
 				}
-				// Candidates first by their code byte (SWAR).  A header's csize is at most max_csize, so its top byte (3
-				// bytes after the code) is small: a second SWAR filter on the bytes already loaded (the next lane holds the
-				// 3 bytes past mine) removes nearly all of the code-byte look-alikes before the chain check, which costs
-				// dependent loads.
-				w[INDEX_SPAN / 4] = __shfl_down_sync(FULL, w[0], 1);
+				// A header's csize is at most max_csize, so its top byte (3 bytes after the code) is small: a second SWAR
+				// filter on the bytes already loaded (the next lane holds the 3 bytes past mine) removes nearly all of the
+				// code-byte look-alikes before the chain check, which costs dependent loads.
+				w[4] = __shfl_down_sync(FULL, w[0], 1);
 				if (lane == 31)
-					w[INDEX_SPAN / 4] = 0u; // unknown: lets the last three positions pass
+					w[4] = 0u; // unknown: lets the last three positions pass
 				if (xb < scan_end) {
+					const uint32_t hi_max = P.max_csize >> 16;
+					const uint32_t kadd = hi_max < 0x7Fu ? (0x7Fu - hi_max) * 0x01010101u : 0u;
 #pragma unroll
-					for (int g = 0; g < INDEX_SPAN / 16 && found == IDX_NONE; ++g) {
-						uint32_t cand = 0;
-#pragma unroll
-						for (int j = 0; j < 4; ++j) {
-							const uint32_t wj = w[4 * g + j];
-							uint32_t z = zero_bytes(wj ^ 0x01010101u) | zero_bytes(wj ^ 0x06060606u) | zero_bytes(wj ^ 0x02020202u);
-							if (hi_max < 0x7Fu) {
-								const uint32_t t3 = __funnelshift_r(wj, w[4 * g + j + 1], 24); // byte b + 3 at position b
-								z &= ~(((t3 & 0x7F7F7F7Fu) + kadd) | t3);
-							}
-							cand |= flags_to_mask4(z) << (4 * j);
+					for (int j = 0; j < 4; ++j) {
+						uint32_t z = zero_bytes(w[j] ^ 0x01010101u) | zero_bytes(w[j] ^ 0x06060606u) | zero_bytes(w[j] ^ 0x02020202u);
+						if (hi_max < 0x7Fu) {
+							const uint32_t t3 = __funnelshift_r(w[j], w[j + 1], 24); // byte b + 3 at position b
+							z &= ~(((t3 & 0x7F7F7F7Fu) + kadd) | t3);
 						}
-						while (cand) {
-							const uint32_t b = (uint32_t)__ffs((int)cand) - 1u;
-							cand &= cand - 1u;
-							const uint64_t x = xb + 16u * g + b;
-							if (x >= scan_end)
-								break;
-							if (index_chain_plausible(P.src, P.src_size, x, P.max_csize)) {
-								found = x;
-								break;
-							}
-						}
+						cand |= flags_to_mask4(z) << (4 * j);
+					}
+				}
+				while (cand) {
+					const uint32_t b = (uint32_t)__ffs((int)cand) - 1u;
+					cand &= cand - 1u;
+					const uint64_t x = xb + b;
+					if (x >= scan_end)
+						break;
+					if (index_chain_plausible(P.src, P.src_size, x, P.max_csize)) {
+						found = x;
+						break;
 					}
 				}
 				const uint32_t m = __ballot_sync(FULL, found != IDX_NONE);
@@ -652,19 +660,6 @@ namespace sb
 		__syncthreads();
 		if (tid == 0)
 			*P.ok = sm[0];
-		if (sm[0]) {
-			// accepted: every segment's headers are walked again (L2 hits) and written at the segment's base -- here, not
-			// in a third launch (index_fill_kernel: 14 us for a frame of 8192 superblocks, most of it the launch)
-			for (uint32_t k = tid; k < P.n_seg; k += blockDim.x) {
-				const uint32_t cnt = P.seg_count[k];
-				uint32_t at_i = P.seg_base[k];
-				unsigned long long pos = P.seg_start[k];
-				for (uint32_t i = 0; i < cnt && at_i < P.n_sb; ++i, ++at_i) {
-					P.sb_offsets[at_i] = pos;
-					pos = index_next(P.src, P.src_size, pos);
-				}
-			}
-		}
 		if (!sm[0] && tid == 0) {
 			// fallback: the serial walk (stenos.cpp:1124-1143)
 			uint64_t at = P.first;
@@ -681,6 +676,21 @@ namespace sb
 			P.sb_offsets[P.n_sb] = at;
 			if (at > P.src_size)
 				atomicOr(&P.result[1], (unsigned long long)DEV_ERR_INVALID_INPUT);
+		}
+	}
+
+	// accepted: every segment walks its headers again (L2 hits) and writes them at its base
+	__global__ void __launch_bounds__(128) index_fill_kernel(FastIndexParams P)
+	{
+		const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+		if (k >= P.n_seg || *P.ok == 0u)
+			return;
+		const uint32_t cnt = P.seg_count[k];
+		uint32_t at_i = P.seg_base[k];
+		unsigned long long pos = P.seg_start[k];
+		for (uint32_t i = 0; i < cnt && at_i < P.n_sb; ++i, ++at_i) {
+			P.sb_offsets[at_i] = pos;
+			pos = index_next(P.src, P.src_size, pos);
 		}
 	}
 

@@ -93,3 +93,37 @@ def make(name, n, T, seed=0):
     else:
         raise ValueError(name)
     return _fit(v, T)
+
+
+# ------------------------------------------------------------------------------------------------
+# frames of level >= 2 (hybrid decoder): inputs on which the reference picks each of its Zstd strategies
+# ------------------------------------------------------------------------------------------------
+def hybrid_cases(n, seed=0):
+    """(name, T, raw uint8 array): text -> code 2 (Zstd) and 3 (Zstd on the transposed input), steps -> 2 and 5 (blocks + Zstd),
+    sensor / sine series -> 4 (transposed + delta + Zstd), small alphabet and walks -> 5."""
+    from stenos_b200 import synth
+    rng = np.random.default_rng(seed)
+    text = np.frombuffer((b"the quick brown fox jumps over the lazy dog, " * (n * 4 // 45 + 2))[: n * 4], dtype=np.uint8)
+    return [
+        ("text", 4, text),
+        ("steps", 4, (np.arange(n) // 1000 * 1000).astype(np.int32).view(np.uint8)),
+        ("float64_sensor", 8, np.ascontiguousarray(synth.make("float64_sensor", n // 2)).view(np.uint8)),
+        ("int16_sine", 2, np.ascontiguousarray(synth.make("int16_sine", n * 2 + 37)).view(np.uint8)),
+        ("alphabet4", 4, rng.integers(0, 4, n * 4, dtype=np.uint8)),
+        ("walk", 8, np.cumsum(rng.integers(-3, 4, n // 2)).astype(np.int64).view(np.uint8)),
+    ]
+
+
+def superblock_codes(frame, T, total):
+    """Histogram of the superblock codes of a frame (host walk, stenos.cpp:1124-1143)."""
+    first = 12 if frame[0] == 255 else 8
+    if frame[0] == 255:
+        sb = int.from_bytes(bytes(frame[8:12]), "little")
+    else:
+        bs = T * 256
+        sb = (bs if bs > 131072 else (131072 // bs) * bs) << int(frame[0])
+    at, out = first, {}
+    for _ in range((total + sb - 1) // sb):
+        out[int(frame[at])] = out.get(int(frame[at]), 0) + 1
+        at += 4 + int.from_bytes(bytes(frame[at + 1:at + 4]), "little")
+    return out

@@ -6,7 +6,7 @@ import pytest
 
 import dists
 import emu_lib
-from oracle import port
+from oracle import port, ref
 from stenos_b200 import api, capi
 
 
@@ -164,7 +164,7 @@ def test_parallel_frame_index_resynchronises_or_falls_back():
         l0 = api.kernel_launches()
         assert ctx.frame_index_async(f, len(frame), 4, offs, n_sb + 1, res) == n_sb
         ctx.synchronize()
-        assert api.kernel_launches() - l0 == 2  # the parallel path (scan, merge + fill), not the serial kernel
+        assert api.kernel_launches() - l0 == 3  # the parallel path (scan + merge + fill), not the serial kernel
         assert res[1] == 0 and np.array_equal(offs, port.frame_index(frame, 4))
         if i == 0:
             assert ctx.index_accepted() == 1  # an ordinary frame must not need the serial fallback
@@ -287,3 +287,70 @@ def test_pipelined_host_decompress(monkeypatch):
     c = port.compress(raw, 4)
     for cut in (len(c) - 5, len(c) // 2):
         assert run(api.decompress, c[:cut], 4, raw.size) == "INVALID_INPUT"
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the compiled reference) writes the level >= 2 frames")
+def test_hybrid_decoder_reads_the_reference_frames_of_every_level():
+    """Frames the REFERENCE writes at levels 2..9 (superblock codes 2..5: host Zstd + device filters / block decoder,
+    stenos.cpp:681-753) decode to the input; superblocks of 128 KiB .. 2 MiB."""
+    ctx = api.Context()
+    seen = {}
+    for name, T, raw in dists.hybrid_cases(70000):
+        for level in (2, 3, 6, 9):
+            frame = np.frombuffer(ref.compress(raw, T, level=level), dtype=np.uint8)
+            for c, k in dists.superblock_codes(frame, T, raw.size).items():
+                seen[c] = seen.get(c, 0) + k
+            assert ctx.decompress(frame, T, raw.size) == raw.tobytes(), (name, level)
+    assert {2, 3, 4, 5} <= set(seen), seen
+    # a damaged Zstd payload is invalid input, not a crash
+    frame = np.frombuffer(ref.compress(dists.hybrid_cases(70000)[0][2], 4, level=3), dtype=np.uint8).copy()
+    frame[12:16] ^= 0x5A  # the Zstd magic number of the first superblock's payload
+    with pytest.raises(api.StenosError):
+        ctx.decompress(frame, 4, 70000 * 4)
+
+
+def _bucket_inputs(T, n_buckets, seed):
+    """runs, noise, steps and constants side by side: buckets that code well, COPY buckets, all-same buckets"""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for b in range(n_buckets):
+        k = b % 4
+        if k == 0:
+            v = dists.make("ramp_noise16", 256, T, seed=seed + b)
+        elif k == 1:
+            v = rng.integers(0, 256, 256 * T, dtype=np.uint8).view({2: np.int16, 4: np.int32, 8: np.int64}[T])
+        elif k == 2:
+            v = np.full(256, 42, dtype={2: np.int16, 4: np.int32, 8: np.int64}[T])
+        else:
+            v = dists.make("sparse_changes", 256, T, seed=seed + b)
+        parts.append(raw_of(v))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_batched_bucket_encode_matches_the_per_bucket_call(T):
+    """stenos_b200_compress_buckets_async == one stenos_private_compress_block per bucket with dst_size = the slot
+    (cvector.hpp:1394-1420; room rule of SURVEY appendix C2), for full, partial-tail and selected (dirty) buckets."""
+    ctx = api.Context()
+    bb = 256 * T
+    raw = _bucket_inputs(T, 13, seed=T)
+    raw = np.concatenate([raw, raw[: bb // 2]])  # a last bucket of half the size
+    n = (raw.size + bb - 1) // bb
+    for stride, ids in ((bb + 16, None), (bb + 12, None), (bb + 16, np.array([3, 0, 13, 7, 7], dtype=np.uint32)), (bb // 2, None)):
+        m = n if ids is None else ids.size
+        slots = np.zeros(m * stride, dtype=np.uint8)
+        sizes = np.zeros(m, dtype=np.uint32)
+        res = np.zeros(2, dtype=np.uint64)
+        ctx.compress_buckets_async(raw, T, bb, raw.size, ids, m, slots, stride, sizes, res)
+        ctx.synchronize()
+        overflow = False
+        for i in range(m):
+            b = int(i if ids is None else ids[i])
+            bucket = raw[b * bb:(b + 1) * bb]
+            want = run(port.compress_superblock, bucket, T, 1, stride)
+            if isinstance(want, str):
+                assert sizes[i] == 0, (T, stride, i)
+                overflow = True
+            else:
+                assert sizes[i] == len(want) and slots[i * stride:i * stride + len(want)].tobytes() == want, (T, stride, i)
+        assert (int(res[1]) & 1) == (1 if overflow else 0)

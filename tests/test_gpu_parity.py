@@ -548,3 +548,85 @@ def test_reference_own_cvector_test_against_the_boundary():
     r = subprocess.run([_ref_program("ref_test_cvector_main_b200")], capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert "ref_test_cvector ok" in r.stdout
+
+
+def test_hybrid_decoder_reads_the_reference_frames_of_every_level():
+    """Frames written by the REFERENCE at levels 2..9 (superblock codes 2..5, superblocks of 128 KiB .. 2 MiB) decode to
+    the input: Zstd on the host (1 and 4 threads), inverse filters and the block decoder on the GPU; host and device
+    resident frames / outputs.  (stenos.cpp:681-753)"""
+    import torch
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref (the compiled reference) writes the frames")
+    ctx = api.Context()
+    seen = {}
+    for name, T, raw in dists.hybrid_cases(1 << 20):
+        for level in range(2, 10):
+            frame = np.frombuffer(ref.compress(raw, T, level=level), dtype=np.uint8)
+            for c, k in dists.superblock_codes(frame, T, raw.size).items():
+                seen[c] = seen.get(c, 0) + k
+            ctx.set_threads(4 if level % 2 else 1)
+            assert ctx.decompress(frame, T, raw.size) == raw.tobytes(), (name, level)
+            if level in (3, 6):
+                d_frame = torch.from_numpy(frame.copy()).cuda()
+                d_out = torch.zeros(raw.size, dtype=torch.uint8, device="cuda")
+                assert ctx.decompress_raw(d_frame, T, frame.size, d_out, raw.size) == raw.size
+                assert bytes(d_out.cpu().numpy()) == raw.tobytes(), (name, level, "device")
+    assert {1, 2, 3, 4, 5} <= set(seen), seen
+    frame = np.frombuffer(ref.compress(dists.hybrid_cases(1 << 18)[2][2], 8, level=5), dtype=np.uint8).copy()
+    frame[12:16] ^= 0x5A  # the Zstd magic number of the first superblock's payload
+    with pytest.raises(api.StenosError):
+        ctx.decompress(frame, 8, (1 << 18) * 4)
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_batched_bucket_encode_matches_the_per_bucket_call(T):
+    """stenos_b200_compress_buckets_async (device resident, one launch) == stenos_private_compress_block per bucket with
+    dst_size = the slot (cvector.hpp:1394-1420, room rule of SURVEY appendix C2); its slots are then read back through
+    stenos_b200_gather_decode_async with the slot offsets as the index."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    bb = 256 * T
+    n = 3000
+    a = synth.make({2: "int16_sine", 4: "int32_ramp_runs", 8: "int64_ramp_runs"}[T], n * 256)
+    raw = raw_of(a).copy()
+    rng = np.random.default_rng(T)
+    for b in rng.integers(0, n, 300):  # incompressible buckets -> COPY
+        raw[b * bb:(b + 1) * bb] = rng.integers(0, 256, bb, dtype=np.uint8)
+    ctx = api.Context(stream=torch.cuda.current_stream())
+    d_src = torch.from_numpy(raw).to(dev)
+    stride = bb + 16
+    d_slots = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+    d_sizes = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    l0 = api.kernel_launches()
+    ctx.compress_buckets_async(d_src, T, bb, raw.size, None, n, d_slots, stride, d_sizes, d_res)
+    torch.cuda.synchronize()
+    assert api.kernel_launches() - l0 == 1
+    assert d_res.cpu().numpy()[1] == 0
+    slots, sizes = d_slots.cpu().numpy(), d_sizes.cpu().numpy()
+    host = api.Context()
+    for i in list(range(0, n, 7)) + [n - 1]:
+        bucket = raw[i * bb:(i + 1) * bb]
+        want = port.compress_superblock(bucket, T, 1, stride)
+        assert sizes[i] == len(want) and slots[i * stride:i * stride + len(want)].tobytes() == want, (T, i)
+        if i % 49 == 0:
+            assert host.compress_block(bucket, T, super_block_size=bb, room=stride) == want
+    # dirty buckets only, then random access to the slots
+    ids = rng.permutation(n)[:500].astype(np.uint32)
+    d_ids = torch.from_numpy(ids.view(np.int32).copy()).to(dev)
+    d_slots2 = torch.zeros(ids.size * stride, dtype=torch.uint8, device=dev)
+    d_sizes2 = torch.zeros(ids.size, dtype=torch.int32, device=dev)
+    ctx.compress_buckets_async(d_src, T, bb, raw.size, d_ids, ids.size, d_slots2, stride, d_sizes2, d_res)
+    torch.cuda.synchronize()
+    s2 = d_slots2.cpu().numpy()
+    for k in range(0, ids.size, 11):
+        i = int(ids[k])
+        assert s2[k * stride:k * stride + sizes[i]].tobytes() == slots[i * stride:i * stride + sizes[i]].tobytes()
+    d_off = (torch.arange(n + 1, dtype=torch.int64, device=dev) * stride).contiguous()
+    d_out = torch.zeros(ids.size * bb, dtype=torch.uint8, device=dev)
+    ctx.gather_decode_async(d_slots, n * stride, T, bb, raw.size, d_off, n, d_ids, ids.size, d_out, d_res)
+    torch.cuda.synchronize()
+    assert d_res.cpu().numpy()[1] == 0
+    assert np.array_equal(d_out.cpu().numpy().reshape(-1, bb), raw.reshape(-1, bb)[ids])

@@ -137,6 +137,39 @@ def row_gather(nbytes, n_ids, dev, pk, steps=5, warmup=3):
             "frac": alg / t / 1e6 / pk, "parity": bool(ok)}
 
 
+def row_buckets(nbytes, dev, pk, steps=5, warmup=3):
+    """cvector<int> write side: every 1 KiB bucket of the array compressed into its slot of 1 KiB + 16 in ONE launch
+    (stenos_b200_compress_buckets_async), then the slots read back at random through the gather decoder."""
+    T, bb = 4, 1024
+    stride = bb + 16
+    ctx = api.Context(level=1, stream=torch.cuda.current_stream())
+    d_src = synth.make_torch("int32_ramp_runs", nbytes // T, device=dev).view(torch.uint8)
+    n_b = nbytes // bb
+    d_slots = torch.empty(n_b * stride, dtype=torch.uint8, device=dev)
+    d_sizes = torch.zeros(n_b, dtype=torch.int32, device=dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    t = timeit(lambda: ctx.compress_buckets_async(d_src, T, bb, nbytes, None, n_b, d_slots, stride, d_sizes, d_res), steps, warmup)
+    ok = int(d_res.cpu()[1]) == 0
+    sizes = d_sizes.cpu().numpy().astype(np.int64)
+    slots = d_slots.cpu().numpy()
+    src = d_src.cpu().numpy()
+    from oracle import port  # the checker
+    for i in np.random.default_rng(7).integers(0, n_b, 64):
+        want = port.compress_superblock(src[i * bb:(i + 1) * bb], T, 1, stride)
+        ok = ok and sizes[i] == len(want) and slots[i * stride:i * stride + len(want)].tobytes() == want
+    # all buckets back through the gather decoder (offset of bucket i = i * stride)
+    d_off = torch.arange(n_b + 1, dtype=torch.int64, device=dev) * stride
+    ids = torch.arange(n_b, dtype=torch.int32, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ctx.gather_decode_async(d_slots, n_b * stride, T, bb, nbytes, d_off, n_b, ids, n_b, d_out, d_res)
+    torch.cuda.synchronize()
+    ok = ok and int(d_res.cpu()[1]) == 0 and torch.equal(d_out, d_src)
+    ctx.close()
+    alg = nbytes + int(sizes.sum())
+    return {"row": "bucket_encode", "T": T, "buckets": int(n_b), "slot_stride": stride, "compressed_bytes": int(sizes.sum()), "algorithmic_bytes": int(alg), "ms": t,
+            "GBps_in": nbytes / t / 1e6, "frac": alg / t / 1e6 / pk, "parity": bool(ok)}
+
+
 def all_rows(dev, stream, pk, steps=5, warmup=3, codec_bytes=1 << 30, filter_bytes=4 << 30, gather_bytes=1 << 30):
     rows = []
     with torch.cuda.stream(stream):
@@ -147,6 +180,8 @@ def all_rows(dev, stream, pk, steps=5, warmup=3, codec_bytes=1 << 30, filter_byt
             rows.append(row_filters(T, name, filter_bytes, 262144, dev, pk, steps, warmup))
             torch.cuda.empty_cache()
         rows.append(row_gather(gather_bytes, 1 << 20, dev, pk, steps, warmup))
+        torch.cuda.empty_cache()
+        rows.append(row_buckets(gather_bytes, dev, pk, steps, warmup))
         torch.cuda.empty_cache()
     return rows
 
@@ -162,7 +197,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, default=1024)
     ap.add_argument("--filter-mib", type=int, default=1024)
-    ap.add_argument("--rows", default="codec,filters,gather")
+    ap.add_argument("--rows", default="codec,filters,gather,buckets")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
@@ -178,6 +213,8 @@ def main():
                 print(json.dumps(row_filters(T, name, args.filter_mib << 20, chunk, dev, pk)), flush=True)
     if "gather" in rows:
         print(json.dumps(row_gather(nbytes, 1 << 20, dev, pk)), flush=True)
+    if "buckets" in rows:
+        print(json.dumps(row_buckets(nbytes, dev, pk)), flush=True)
 
 
 if __name__ == "__main__":
