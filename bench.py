@@ -9,7 +9,8 @@ reference-facing C ABI call (stenos_compress_generic) on pinned HOST buffers, co
 
 N = 1: BASELINE.json configs[1] -- 1 GiB int32 (noisy ramp + runs), level 1.  The line also carries `rows` for the
 other configs of SURVEY.md section 8(d): the codec on T = 2 (int16 sine) and T = 8 (int64 ramp + runs) at 1 GiB,
-the filters on the 4 GiB float64 / float32 / int16 series (config 3), the 2^20-bucket gather (config 5); and
+the filters on the 4 GiB float64 / float32 / int16 series (config 3), the 2^20-bucket gather (config 5), the batched
+bucket encode (cvector write side) and the hybrid level-3 path (device filters + host Zstd) next to the reference; and
 `stream_parity`: superblocks of the very stream that was timed, compared byte for byte with the CPU oracle.
 
 N > 1 (torchrun, one process per GPU): BASELINE.json configs[3] -- 16 GiB int16 + 16 GiB int64, each its own

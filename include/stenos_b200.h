@@ -150,6 +150,17 @@ STENOS_B200_EXPORT size_t stenos_b200_unshuffle(stenos_context* ctx, size_t byte
 STENOS_B200_EXPORT size_t stenos_b200_delta(stenos_context* ctx, size_t bytes, size_t chunk, const void* src, void* dst);
 STENOS_B200_EXPORT size_t stenos_b200_delta_inv(stenos_context* ctx, size_t bytes, size_t chunk, const void* src, void* dst);
 
+/* Hybrid level >= 2, first slice.  DECODING is complete: stenos_decompress[_generic] reads
+ * every frame the reference writes at levels 2..9 for bytesoftype in {2,4,8} (superblock codes 2..5 of
+ * stenos.cpp:34-39: Zstd on the host threads of stenos_set_threads, inverse filters and block decoder on the device).
+ * ENCODING with a forced strategy: every superblock as code 3 (Zstd over the shuffled input, stenos.cpp:617-634) or
+ * code 4 (Zstd over the shuffled + byte-delta input, :636-656), level in 2..9 (superblock size and Zstd level as the
+ * reference maps them); the reference's own choice between strategies (lz4_guess_ratio, :492-558) is not made here,
+ * so stenos_compress with level >= 2 still returns STENOS_ERROR_INVALID_PARAMETER.  Where the reference picks the
+ * forced strategy for every superblock the frames are identical.  Host or device pointers; synchronous. */
+STENOS_B200_EXPORT size_t stenos_b200_compress_strategy(stenos_context* ctx, const void* src, size_t bytesoftype, size_t bytes, void* dst, size_t dst_size, int level,
+						       int strategy);
+
 /* stenos::cvector random access (BASELINE.json config 5): a serialized cvector is a frame with
  * shift 255 whose superblocks are the buckets (cvector.hpp:3034-3093).  Given the bucket header
  * offsets (stenos_b200_frame_index_async) decode n buckets, chosen by d_bucket_ids, into a dense

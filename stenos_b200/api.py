@@ -169,6 +169,15 @@ class Context:
         """1: the last parallel frame index was accepted, 0: it fell back to the serial walk, -1: none ran."""
         return int(self._lib.stenos_b200_index_accepted(self._h))
 
+    def compress_strategy(self, buf, bytesoftype, level, strategy, dst_size=None):
+        """Level >= 2 with a forced strategy: 3 = Zstd(shuffle), 4 = Zstd(delta(shuffle)) (stenos.cpp:617-656)."""
+        src = as_u8(buf)
+        if dst_size is None:
+            dst_size = bound(src.size)
+        dst = np.empty(max(dst_size, 1), dtype=np.uint8)
+        r = check(self._lib.stenos_b200_compress_strategy(self._h, ptr_of(src), bytesoftype, src.size, ptr_of(dst), dst_size, level, strategy), "stenos_b200_compress_strategy")
+        return dst[:r].tobytes()
+
     def compress_buckets_async(self, d_src, bytesoftype, bucket_bytes, total_bytes, d_ids, n, d_slots, slot_stride, d_sizes, d_result):
         """n cvector buckets in one launch (cvector.hpp:1394-1420): bare superblocks in fixed slots + their sizes."""
         return check(self._lib.stenos_b200_compress_buckets_async(self._h, ptr_of(d_src), bytesoftype, bucket_bytes, total_bytes, ptr_of(d_ids), n, ptr_of(d_slots), slot_stride,

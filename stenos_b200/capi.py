@@ -61,6 +61,7 @@ SIGNATURES = {
     "stenos_b200_delta": (_sz, [_vp, _sz, _sz, _vp, _vp]),
     "stenos_b200_delta_inv": (_sz, [_vp, _sz, _sz, _vp, _vp]),
     "stenos_b200_gather_decode_async": (_sz, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "stenos_b200_compress_strategy": (_sz, [_vp, _vp, _sz, _sz, _vp, _sz, C.c_int, C.c_int]),
     "stenos_b200_compress_buckets_async": (_sz, [_vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "stenos_b200_synchronize": (_sz, [_vp]),
     "stenos_b200_test_occupy": (_sz, [_vp, _ci, C.c_uint, C.c_ulonglong]),

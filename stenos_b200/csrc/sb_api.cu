@@ -40,6 +40,8 @@ namespace
 	zstd_compress_fn p_zstd_compress = nullptr;
 	zstd_decompress_fn p_zstd_decompress = nullptr;
 	zstd_iserror_fn p_zstd_iserror = nullptr;
+	typedef int (*zstd_maxclevel_fn)(void);
+	zstd_maxclevel_fn p_zstd_maxclevel = nullptr;
 	bool load_zstd()
 	{
 		static std::atomic<int> state{ 0 }; // 0 untried, 1 ok, 2 missing
@@ -50,6 +52,7 @@ namespace
 				p_zstd_compress = (zstd_compress_fn)dlsym(h, "ZSTD_compress");
 				p_zstd_decompress = (zstd_decompress_fn)dlsym(h, "ZSTD_decompress");
 				p_zstd_iserror = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
+				p_zstd_maxclevel = (zstd_maxclevel_fn)dlsym(h, "ZSTD_maxCLevel");
 			}
 			s = (p_zstd_compress && p_zstd_decompress && p_zstd_iserror) ? 1 : 2;
 			state.store(s);
@@ -415,10 +418,10 @@ namespace
 #define FLOW_KB_2 8
 #endif
 #ifndef FLOW_KB_4
-#define FLOW_KB_4 3
+#define FLOW_KB_4 4
 #endif
 #ifndef FLOW_KB_8
-#define FLOW_KB_8 2
+#define FLOW_KB_8 4
 #endif
 	// encode_flow_kernel (sb_flow.cuh): the default fast path
 	template<int T, int NT, int KB>
@@ -2259,9 +2262,158 @@ namespace
 		}
 		return (size_t)total;
 	}
+
+	// ------------------------------------------------------------------------------------------
+	// Hybrid encoder of level >= 2 with a FORCED strategy (first slice): every superblock as
+	// TRANSPOSED_ZSTD (code 3, stenos.cpp:617-634) or TRANSPOSED_DELTA_ZSTD (code 4, :636-656) -- the shuffle (+ byte
+	// delta) of the whole input in one device launch, chunk = the level's superblock (prepare(), :159-162), Zstd per
+	// superblock on the host threads at the reference's level mapping (:448-456, zstd_wrapper.h:49-56).  What is NOT
+	// here is the reference's choice between its strategies (lz4_guess_ratio, :492-558): on inputs where the reference
+	// picks the forced strategy for every superblock the frame is identical, byte for byte (tests).
+	// ------------------------------------------------------------------------------------------
+	size_t compress_strategy_impl(stenos_context* ctx, const uint8_t* src, size_t T, size_t bytes, uint8_t* dst, size_t dst_size, int level, int strategy)
+	{
+		if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
+			return STENOS_ERROR_INVALID_BYTESOFTYPE;
+		if (!supported_T(T) || level < 2 || level > 9 || (strategy != 3 && strategy != 4) || bytes % T != 0 || ctx->custom_shift != STENOS_NO_BLOCK_SHIFT || ctx->max_ns != 0)
+			return STENOS_ERROR_INVALID_PARAMETER;
+		if (!ctx->activate())
+			return STENOS_ERROR_ALLOC;
+		if (!load_zstd() || !p_zstd_maxclevel)
+			return STENOS_ERROR_ZSTD_INTERNAL;
+		cudaStream_t st = ctx->stream();
+		const bool src_dev = is_device_ptr(src), dst_dev = is_device_ptr(dst);
+		// prepare(), stenos.cpp:159-162
+		size_t sb = default_superblock(T);
+		int shift = 0;
+		if (bytes > sb) {
+			shift = (level - 1) / 2;
+			sb <<= (size_t)shift;
+		}
+		if (dst_size < 8)
+			return STENOS_ERROR_DST_OVERFLOW;
+		// level -> Zstd level (stenos.cpp:448-456: level - 1, skipping 4; zstd_wrapper.h:49-56)
+		int reduced = level - 1;
+		if (reduced >= 4)
+			++reduced;
+		const int zlevel = reduced < 1 ? 1 : (reduced < 9 ? 2 * reduced - 1 : p_zstd_maxclevel());
+		const size_t n_sb = (bytes + sb - 1) / sb;
+		std::vector<uint8_t> frame_host;
+		uint8_t* out = dst;
+		if (dst_dev) {
+			frame_host.resize(std::min<size_t>(dst_size, 8 + bytes + 4 * n_sb + 64));
+			out = frame_host.data();
+		}
+		const size_t out_cap = dst_dev ? frame_host.size() : dst_size;
+		write_frame_header(out, shift, bytes, sb, false);
+		size_t total = 8;
+		if (bytes == 0)
+			goto done;
+		{
+			// ---- the filter on the device, back to the host
+			std::unique_ptr<uint8_t[]> filt(new (std::nothrow) uint8_t[bytes]);
+			if (!filt || !ctx->hyb.reserve(bytes + 32))
+				return STENOS_ERROR_ALLOC;
+			const size_t fr = filter_impl(ctx, OP_SHUFFLE, T, bytes, sb, src, ctx->hyb.p, strategy == 4 ? 1 : 0);
+			if (is_err(fr))
+				return fr;
+			cudaMemcpyAsync(filt.get(), ctx->hyb.p, bytes, cudaMemcpyDeviceToHost, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+			// ---- Zstd per superblock
+			struct Piece
+			{
+				std::unique_ptr<uint8_t[]> z; // (not a vector: no zero fill of the worst case)
+				size_t len = 0;
+				unsigned code = 0;
+			};
+			std::vector<Piece> pieces(n_sb);
+			std::atomic<size_t> next(0), failed(0);
+			auto raw_of = [&](size_t i, size_t n, std::vector<uint8_t>& tmp) -> const uint8_t* {
+				if (!src_dev)
+					return src + i * sb;
+				tmp.resize(n);
+				cudaMemcpy(tmp.data(), src + i * sb, n, cudaMemcpyDeviceToHost);
+				return tmp.data();
+			};
+			auto work = [&]() {
+				for (;;) {
+					const size_t i = next.fetch_add(1);
+					if (i >= n_sb || failed.load())
+						return;
+					const size_t n = std::min(sb, bytes - i * sb);
+					Piece& pc = pieces[i];
+					std::vector<uint8_t> tmp;
+					const uint8_t* in = filt.get() + i * sb;
+					unsigned code = (unsigned)strategy;
+					int zl = zlevel;
+					if (n < 128) { // stenos.cpp:435-437: a tiny superblock is Zstd on the raw bytes, zstd_level 0 -> 1
+						in = raw_of(i, n, tmp);
+						code = (unsigned)CODE_ZSTD;
+						zl = 1;
+					}
+					const size_t cap = n + n / 128 + 512;
+					pc.z.reset(new (std::nothrow) uint8_t[cap]);
+					if (!pc.z) {
+						failed.store(STENOS_ERROR_ALLOC);
+						return;
+					}
+					const size_t zr = p_zstd_compress(pc.z.get(), cap, in, n, zl);
+					if (p_zstd_iserror(zr) || zr > n) { // :627-628 -> MEMCPY (:363-374)
+						const uint8_t* raw = raw_of(i, n, tmp);
+						memcpy(pc.z.get(), raw, n);
+						pc.len = n;
+						pc.code = (unsigned)CODE_COPY;
+					}
+					else {
+						pc.len = zr;
+						pc.code = code;
+					}
+				}
+			};
+			{
+				const size_t nt = std::min<size_t>(std::max(1, ctx->threads), std::min<size_t>(n_sb, 256));
+				std::vector<std::thread> pool;
+				for (size_t t = 1; t < nt; ++t)
+					pool.emplace_back(work);
+				work();
+				for (auto& t : pool)
+					t.join();
+			}
+			if (failed.load())
+				return failed.load();
+			for (size_t i = 0; i < n_sb; ++i) {
+				const Piece& pc = pieces[i];
+				if (total + 4 + pc.len > out_cap)
+					return STENOS_ERROR_DST_OVERFLOW; // :629-630
+				out[total] = (uint8_t)pc.code;
+				out[total + 1] = (uint8_t)pc.len;
+				out[total + 2] = (uint8_t)(pc.len >> 8);
+				out[total + 3] = (uint8_t)(pc.len >> 16);
+				memcpy(out + total + 4, pc.z.get(), pc.len);
+				total += 4 + pc.len;
+			}
+		}
+	done:
+		if (dst_dev) {
+			cudaMemcpyAsync(dst, out, total, cudaMemcpyHostToDevice, st);
+			if (cudaStreamSynchronize(st) != cudaSuccess) {
+				cudaGetLastError();
+				return STENOS_ERROR_UNDEFINED;
+			}
+		}
+		return total;
+	}
 }
 
 extern "C" {
+
+size_t stenos_b200_compress_strategy(stenos_context* ctx, const void* src, size_t T, size_t bytes, void* dst, size_t dst_size, int level, int strategy)
+{
+	return guarded([&]() -> size_t { return compress_strategy_impl(ctx, static_cast<const uint8_t*>(src), T, bytes, static_cast<uint8_t*>(dst), dst_size, level, strategy); });
+}
 
 size_t stenos_b200_shuffle(stenos_context* ctx, size_t T, size_t bytes, size_t chunk, const void* src, void* dst, int with_delta)
 {

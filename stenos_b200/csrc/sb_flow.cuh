@@ -102,8 +102,8 @@ namespace sb
 		static constexpr uint32_t IN_STRIDE = FLOW_STAGING == 2 ? 32u * 16u * T : 0u;
 		static constexpr uint32_t STAGE_OFF = IN_OFF + NW * IN_STRIDE;
 		static constexpr uint32_t SMEM_TOTAL = 227u * 1024u;
-		// per-half staging ring: a piece (<= KMAX worst blocks) plus the linear tail a block may need before the wrap
-		static constexpr uint32_t REG_MIN = (KMAX + 1u) * ROOM;
+		// per-half staging ring: at least two worst-case blocks (a piece that outgrows its ring continues in its spill slot)
+		static constexpr uint32_t REG_MIN = 2u * ROOM;
 		static constexpr uint32_t REG = ((SMEM_TOTAL - STAGE_OFF - 32u) / NH) & ~15u;
 		static_assert(REG >= REG_MIN, "staging ring too small for this block size / warp count");
 		static constexpr uint32_t smem_bytes() { return STAGE_OFF + NH * REG + 32u; }
@@ -968,9 +968,32 @@ namespace sb
 		// room for one more block in both rings: the oldest pieces move to their spill slots -- never a wait: the superblock
 		// they belong to may be waiting for the task I am working on.  (Placed pieces leave at the top of every task, so a
 		// ring that fills up in the middle of one holds pieces that are not placed yet.)
+		// my half's piece in the making: where it starts in the ring, its bytes before / after the ring's wrap, and the
+		// bytes of it that already moved to its spill slot (pieces are not bounded by the ring: K worst-case blocks may be
+		// several times its size, typical data needs a fraction of it)
+		uint32_t posA = 0, lenA = 0, lenB = 0, sp_len = 0;
+		bool wrapped = false;
+		// appends what the ring holds of the piece in the making to its spill slot (the slot of the entry it will get)
+		auto flush_current = [&]() {
+			uint8_t* to = spill + (size_t)(pq_tail % FLOW_PQ) * L::SPILL_SLOT + sp_len;
+			half_copy_from_smem(to, smem, stage + posA, lenA, r);
+			if (lenB)
+				half_copy_from_smem(to + lenA, smem, stage, lenB, r);
+			sp_len += lenA + lenB;
+			lenA = 0;
+			lenB = 0;
+			wrapped = false;
+			posA = pos;
+			vtail = vcur; // nothing older is left in the ring (see make_room)
+			__syncwarp();
+		};
 		auto make_room = [&](bool need) {
-			while (__any_sync(FULL, need && vcur + L::ROOM - vtail > REG))
-				spill_one();
+			while (__any_sync(FULL, need && vcur + L::ROOM - vtail > REG)) {
+				if (pq_ring != pq_tail)
+					spill_one();
+				else
+					flush_current(); // the piece in the making is what fills the rings
+			}
 		};
 
 		uint32_t t = try_take();
@@ -1041,8 +1064,8 @@ namespace sb
 			const uint32_t cnt = b0 < nfull ? min(K, nfull - b0) : 0u;
 			const uint8_t* blk = in + (uint64_t)b0 * L::BLOCK;
 
-			uint32_t posA = pos, lenA = 0, lenB = 0;
-			bool wrapped = false;
+			posA = pos, lenA = 0, lenB = 0, sp_len = 0;
+			wrapped = false;
 			uint32_t tnext = NO_TASK; // my warp's next task, taken during the last block of this one
 			const uint32_t kmax = max(1u, __reduce_max_sync(FULL, cnt));
 			for (uint32_t it = 0; it < kmax; ++it) {
@@ -1116,6 +1139,11 @@ namespace sb
 			}
 
 			// ---- publish my piece; the placer puts the superblock in the frame once all pieces are there
+			const bool in_spill = __any_sync(FULL, sp_len != 0u); // (both halves' pieces of a task move together)
+			if (in_spill) {
+				flush_current(); // the rest of it: the whole piece sits in its spill slot
+				lenA = sp_len;
+			}
 			if (r == 0) {
 				uint32_t* pf = pinfo + (pq_tail % FLOW_PQ) * 4u;
 				st_vol_u32(pf + 0, posA);
@@ -1127,6 +1155,8 @@ namespace sb
 			if (lane == 0)
 				st_vol_u32(pmeta + pq_tail % FLOW_PQ, t);
 			++pq_tail;
+			if (in_spill)
+				pq_ring = pq_tail; // [pq_head, pq_ring) are the spilled entries: this one joins them (pq_ring was pq_tail already)
 			__syncwarp();
 			__threadfence_block();
 			uint32_t na = 0;

@@ -354,3 +354,29 @@ def test_batched_bucket_encode_matches_the_per_bucket_call(T):
             else:
                 assert sizes[i] == len(want) and slots[i * stride:i * stride + len(want)].tobytes() == want, (T, stride, i)
         assert (int(res[1]) & 1) == (1 if overflow else 0)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the compiled reference) writes the frames to compare with")
+def test_forced_strategy_frames_equal_the_reference_where_it_picks_that_strategy():
+    """stenos_b200_compress_strategy (device shuffle / shuffle + delta, host Zstd; stenos.cpp:617-656): wherever the
+    reference codes EVERY superblock of a frame with strategy 3 or 4, the forced-strategy frame is the same bytes
+    (superblock size and Zstd level of each level included); any forced frame decodes with the reference."""
+    ctx = api.Context()
+    ctx.set_threads(2)
+    hits = {3: 0, 4: 0}
+    for name, T, raw in dists.hybrid_cases(60000):
+        for level in (3, 5, 6, 9):
+            want = ref.compress(raw, T, level=level)
+            codes = dists.superblock_codes(np.frombuffer(want, dtype=np.uint8), T, raw.size)
+            for strat in (3, 4):
+                got = ctx.compress_strategy(raw, T, level, strat)
+                if set(codes) <= {strat}:
+                    assert got == want, (name, level, strat)
+                    hits[strat] += 1
+                elif level == 5:
+                    assert ref.decompress(got, T, raw.size) == raw.tobytes(), (name, level, strat)
+                    assert ctx.decompress(np.frombuffer(got, dtype=np.uint8), T, raw.size) == raw.tobytes()
+    assert hits[3] >= 1 and hits[4] >= 8, hits
+    assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 1, 4) == "INVALID_PARAMETER"
+    assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 3, 5) == "INVALID_PARAMETER"
+    assert run(ctx.compress_strategy, raw_of(np.arange(100000, dtype=np.int32)), 4, 3, 4, 100) == "DST_OVERFLOW"

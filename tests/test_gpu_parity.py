@@ -630,3 +630,32 @@ def test_batched_bucket_encode_matches_the_per_bucket_call(T):
     torch.cuda.synchronize()
     assert d_res.cpu().numpy()[1] == 0
     assert np.array_equal(d_out.cpu().numpy().reshape(-1, bb), raw.reshape(-1, bb)[ids])
+
+
+def test_forced_strategy_frames_equal_the_reference_where_it_picks_that_strategy():
+    """stenos_b200_compress_strategy on the GPU (shuffle / shuffle + delta kernels, host Zstd; stenos.cpp:617-656): the
+    config-3 series (float64 / float32 sensor, int16 sine -- the reference codes them as strategy 4 at every level >= 3)
+    give the reference's frames byte for byte; device resident input and output too."""
+    import torch
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref (the compiled reference) writes the frames to compare with")
+    ctx = api.Context()
+    ctx.set_threads(8)
+    hits = 0
+    for name, T in (("float64_sensor", 8), ("float32_sensor", 4), ("int16_sine", 2)):
+        raw = raw_of(synth.make(name, (3 << 20) // T + 256))
+        for level in (3, 4, 5, 7, 9):
+            want = ref.compress(raw, T, level=level, threads=4)
+            codes = dists.superblock_codes(np.frombuffer(want, dtype=np.uint8), T, raw.size)
+            got = ctx.compress_strategy(raw, T, level, 4)
+            if set(codes) <= {4}:
+                assert got == want, (name, level)
+                hits += 1
+            assert ref.decompress(got, T, raw.size) == raw.tobytes()
+            assert ctx.decompress(np.frombuffer(got, dtype=np.uint8), T, raw.size) == raw.tobytes()
+        d_src = torch.from_numpy(raw.copy()).cuda()
+        d_dst = torch.zeros(api.bound(raw.size), dtype=torch.uint8, device="cuda")
+        r = capi.lib().stenos_b200_compress_strategy(ctx._h, d_src.data_ptr(), T, raw.size, d_dst.data_ptr(), d_dst.numel(), 5, 4)
+        assert r == len(ctx.compress_strategy(raw, T, 5, 4)) and bytes(d_dst[:r].cpu().numpy()) == ctx.compress_strategy(raw, T, 5, 4)
+    assert hits >= 12, hits

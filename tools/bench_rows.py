@@ -170,19 +170,59 @@ def row_buckets(nbytes, dev, pk, steps=5, warmup=3):
             "GBps_in": nbytes / t / 1e6, "frac": alg / t / 1e6 / pk, "parity": bool(ok)}
 
 
+def row_hybrid(name, T, nbytes, level=3, strategy=4):
+    """Level >= 2, first slice of SURVEY 8 f1: forced-strategy compress (device shuffle + delta, host Zstd) and the hybrid decoder, host
+    buffers in and out, next to the reference on the same host threads (its Zstd stage is the same library).  The frame must be the
+    reference's own, byte for byte, where the reference picks that strategy for every superblock (config 3: it does)."""
+    import time
+    from oracle import ref  # comparison arm and checker
+
+    def best(fn, n=3):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            r = fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts), r
+
+    threads = os.cpu_count() or 1
+    raw = np.ascontiguousarray(synth.make(name, nbytes // T)).view(np.uint8)
+    ctx = api.Context()
+    ctx.set_threads(threads)
+    ctx.compress_strategy(raw[: 1 << 22], T, level, strategy)  # warm-up: context buffers, libzstd
+    tc, frame = best(lambda: ctx.compress_strategy(raw, T, level, strategy))
+    fr = np.frombuffer(frame, dtype=np.uint8)
+    td, out = best(lambda: ctx.decompress(fr, T, raw.size))
+    ok = out == raw.tobytes()
+    trc, rframe = best(lambda: ref.compress(raw, T, level=level, threads=threads))
+    raw2 = raw[: raw.size - T]  # (the reference cannot decode sizes that are a multiple of the superblock: SURVEY appendix C1)
+    rf2 = ref.compress(raw2, T, level=level, threads=threads)
+    trd, _ = best(lambda: ref.decompress(rf2, T, raw2.size, threads=threads))
+    ctx.close()
+    return {"row": "hybrid_level%d" % level, "data": name, "T": T, "bytes": int(raw.size), "strategy": strategy, "host_threads": threads,
+            "frame_identical_to_reference": frame == rframe, "parity": bool(ok), "ratio": raw.size / len(frame), "compress_GBps": raw.size / tc / 1e9,
+            "decompress_GBps": raw.size / td / 1e9, "reference_compress_GBps": raw.size / trc / 1e9, "reference_decompress_GBps": raw2.size / trd / 1e9,
+            "note": "host Zstd bound on both sides; the device part is the filter (rows `filters`)"}
+
+
 def all_rows(dev, stream, pk, steps=5, warmup=3, codec_bytes=1 << 30, filter_bytes=4 << 30, gather_bytes=1 << 30):
+    """Every row; a row that fails is reported as {"row": ..., "error": ...} instead of taking the bench line down with it."""
+    jobs = []
+    for T, name in ((2, "int16_sine"), (8, "int64_ramp_runs")):
+        jobs.append(("codec", lambda T=T, name=name: row_codec(T, name, codec_bytes, dev, pk, steps, warmup)))
+    for T, name in ((8, "float64_sensor"), (4, "float32_sensor"), (2, "int16_sine")):
+        jobs.append(("filters", lambda T=T, name=name: row_filters(T, name, filter_bytes, 262144, dev, pk, steps, warmup)))
+    jobs.append(("gather", lambda: row_gather(gather_bytes, 1 << 20, dev, pk, steps, warmup)))
+    jobs.append(("bucket_encode", lambda: row_buckets(gather_bytes, dev, pk, steps, warmup)))
+    jobs.append(("hybrid_level3", lambda: row_hybrid("float64_sensor", 8, 64 << 20)))
     rows = []
     with torch.cuda.stream(stream):
-        for T, name in ((2, "int16_sine"), (8, "int64_ramp_runs")):
-            rows.append(row_codec(T, name, codec_bytes, dev, pk, steps, warmup))
+        for name, job in jobs:
+            try:
+                rows.append(job())
+            except Exception as e:  # noqa: BLE001 -- reported, not hidden
+                rows.append({"row": name, "error": "%s: %s" % (type(e).__name__, e)})
             torch.cuda.empty_cache()
-        for T, name in ((8, "float64_sensor"), (4, "float32_sensor"), (2, "int16_sine")):
-            rows.append(row_filters(T, name, filter_bytes, 262144, dev, pk, steps, warmup))
-            torch.cuda.empty_cache()
-        rows.append(row_gather(gather_bytes, 1 << 20, dev, pk, steps, warmup))
-        torch.cuda.empty_cache()
-        rows.append(row_buckets(gather_bytes, dev, pk, steps, warmup))
-        torch.cuda.empty_cache()
     return rows
 
 
@@ -197,7 +237,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, default=1024)
     ap.add_argument("--filter-mib", type=int, default=1024)
-    ap.add_argument("--rows", default="codec,filters,gather,buckets")
+    ap.add_argument("--rows", default="codec,filters,gather,buckets,hybrid")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
@@ -215,6 +255,9 @@ def main():
         print(json.dumps(row_gather(nbytes, 1 << 20, dev, pk)), flush=True)
     if "buckets" in rows:
         print(json.dumps(row_buckets(nbytes, dev, pk)), flush=True)
+    if "hybrid" in rows:
+        for name, T in (("float64_sensor", 8), ("int16_sine", 2)):
+            print(json.dumps(row_hybrid(name, T, 256 << 20)), flush=True)
 
 
 if __name__ == "__main__":
