@@ -478,7 +478,7 @@ def main():
         "decompress_with_header_walk_GBps": (job_bytes / (dw_ms / args.steps * 1e-3) / 1e9) if dw_ms else None,
         "ratio": my_bytes / float(sum(csizes)), "compressed_bytes_per_gpu": int(sum(csizes)),
         "stream_parity": par_ok, "stream_parity_superblocks": par_n,
-        "roofline": {"bound": "hbm", "kernel": "encode_flow_kernel<4,576,3>" if world == 1 else "encode_flow_kernel<2,...> + <8,...> (one launch per frame)",
+        "roofline": {"bound": "hbm", "kernel": "encode_flow_kernel<4,576,4>" if world == 1 else "encode_flow_kernel<2,...> + <8,...> (one launch per frame)",
                      "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
         "roofline_decompress": {"bound": "hbm", "kernel": "decode_pairs_kernel (with the encoder's superblock index)", "achieved": alg_bytes / (float(np.mean(d_per)) * 1e-3) / 1e9,
