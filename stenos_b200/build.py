@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstenos_b200.so")
 SOURCES = ["sb_api.cu"]
-HEADERS = ["sb_common.cuh", "sb_encode.cuh", "sb_encode_rows.cuh", "sb_decode.cuh", "sb_decode_rows.cuh", "sb_decode_split.cuh", "sb_kernels.cuh", "sb_stream.cuh", "sb_flow.cuh", "sb_filters.cuh", os.path.join("..", "..", "include", "stenos_b200.h")]
+HEADERS = ["sb_common.cuh", "sb_encode.cuh", "sb_encode_rows.cuh", "sb_decode.cuh", "sb_decode_rows.cuh", "sb_kernels.cuh", "sb_stream.cuh", "sb_flow.cuh", "sb_filters.cuh", os.path.join("..", "..", "include", "stenos_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -22,7 +22,6 @@
 #include "sb_stream.cuh"
 #include "sb_flow.cuh"
 #include "sb_decode_rows.cuh"
-#include "sb_decode_split.cuh"
 #include "sb_filters.cuh"
 #include "../../include/stenos_b200.h"
 
@@ -524,47 +523,6 @@ namespace
 			{
 				// experiment knob: fewer resident CTAs per SM than the occupancy allows
 				static const int cap = [] { const char* e = getenv("STENOS_B200_DECODE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-				const char* split_env = getenv("STENOS_B200_SPLIT_DECODER"); // experimental: sb_decode_split.cuh
-				const int split_off = split_env && split_env[0] == '1' ? 0 : 1;
-				if (!split_off) {
-					// parser threads walk the block streams, half-warps decode single blocks behind them (sb_decode_split.cuh)
-					const uint32_t block = (uint32_t)T * 256u;
-					const uint64_t span = std::min<uint64_t>(P.sb_bytes, P.total);
-					SplitParams S;
-					S.kmax = (uint32_t)((span + block - 1) / block);
-					if (S.kmax == 0)
-						S.kmax = 1;
-					const size_t ent_bytes = (size_t)P.n_sb * S.kmax * sizeof(unsigned long long);
-					if (!ctx->blk.reserve(ent_bytes))
-						return STENOS_ERROR_ALLOC;
-					S.d = Q;
-					S.entries = reinterpret_cast<unsigned long long*>(ctx->blk.p);
-					S.n_parse_cta = (P.n_sb + DECODE2_WARPS * 32 - 1) / (DECODE2_WARPS * 32);
-					{
-						const char* e = getenv("STENOS_B200_SPLIT_MODE"); // experiments: 1 parse only, 2 decode only (entries of the last run)
-						S.parse_only = e ? (uint32_t)atoi(e) : 0u;
-					}
-					if (S.parse_only != 2u)
-						cudaMemsetAsync(ctx->blk.p, 0, ent_bytes, ctx->stream());
-					const uint32_t smem = DECODE2_WARPS * 512 + 16 + DECODE2_WARPS * 32 * 4;
-#ifndef STENOS_EMU
-					if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_split_kernel<T>, DECODE2_WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
-						cudaGetLastError();
-						per_sm = 1;
-					}
-#endif
-					if (cap > 0)
-						per_sm = std::min(per_sm, cap);
-					const unsigned long long units = (unsigned long long)P.n_sb * S.kmax;
-					const unsigned long long need = ((units + 1) / 2 + DECODE2_WARPS - 1) / DECODE2_WARPS;
-					// every decoder CTA is resident next to the parsers from the start (their unit pairs are assigned round robin)
-					const unsigned long long room = (unsigned long long)ctx->sm_count * per_sm;
-					const unsigned long long dec_max = room > S.n_parse_cta + 1ull ? room - S.n_parse_cta : 1ull;
-					const unsigned grid = S.n_parse_cta + (unsigned)std::min<unsigned long long>(need, dec_max);
-					STENOS_LAUNCH(decode_split_kernel<T>, dim3(grid), dim3(DECODE2_WARPS * 32), smem, ctx->stream(), S);
-					++g_launches;
-					return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
-				}
 #ifndef STENOS_EMU
 				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_pairs_kernel<T>, DECODE2_WARPS * 32, DECODE2_WARPS * (512 + 128)) != cudaSuccess || per_sm < 1) {
 					cudaGetLastError();

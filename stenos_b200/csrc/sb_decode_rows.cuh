@@ -312,7 +312,6 @@ namespace sb
 		return (((x & 0x00FF00FFu) + (y & sel)) & 0x00FF00FFu) | (x & y & 0x01000100u);
 	}
 
-#ifndef DECODE_ROWS_TWO_PHASE
 	// One full plane-coded block per half-warp: p -> 256 elements at out.  live: the lane's half has a block here.
 	// Returns the bytes consumed (uniform over the half-warp), 0xFFFFFFFF for an invalid plane kind.
 	template<int T>
@@ -356,252 +355,6 @@ namespace sb
 		return bad ? 0xFFFFFFFFu : (uint32_t)(q - p);
 	}
 
-#else
-	// One full plane-coded block per half-warp: p -> 256 elements at out.  live: the lane's half has a block here.
-	// Returns the bytes consumed (uniform over the half-warp), 0xFFFFFFFF for an invalid plane kind.
-	//
-	// (Experimental, -DDECODE_ROWS_TWO_PHASE: measured 0.66 ms against 0.62 ms of the plane-by-plane decoder on the
-	// 1 GiB int32 workload -- fewer stalls per instruction, but 20 % more instructions.)
-	// Two phases.  WALK: the planes in order, only what fixes where things are -- row headers, the mins' length, the
-	// row offsets (a 4-step scan; RLE rows, whose length is data dependent, resolved in row order) -- i.e. the serial
-	// chain of the format and nothing else.  ROWS: with every row's address known, the row loads of all T planes
-	// are issued together and the planes unpack, sum and transpose as independent instruction streams; the
-	// row-to-row carries of two planes share one scan (compose_maps2).
-	template<int T>
-	__device__ __forceinline__ uint32_t decode_block_rows(const uint8_t* p, bool live, int r, int hsh, uint8_t* out)
-	{
-		constexpr uint32_t HS = (T + 1) / 2;
-		const uint32_t below = (1u << r) - 1u;
-		uint32_t kinds = 0;
-		if (live) {
-#pragma unroll
-			for (uint32_t i = 0; i < HS; ++i)
-				kinds |= (uint32_t)p[i] << (8 * i);
-		}
-		// ---- WALK
-		uint32_t H[T], RA[T], MA[T], MK[T]; // row header, offset of the row payload, offset of the min (0: none), RLE mask
-		uint32_t qo = HS;
-		uint32_t coded = 0; // planes that are NORMAL / NORMAL_RLE in at least one half of the warp
-		bool bad = false;
-#pragma unroll
-		for (int pl = 0; pl < T; ++pl) {
-			const uint32_t kind = (kinds >> (4 * pl)) & 15u;
-			const bool normal = live && (kind == (uint32_t)KIND_NORMAL || kind == (uint32_t)KIND_NORMAL_RLE);
-			// a RAW plane is 16 raw rows; an ALL_SAME plane is 16 rows of width 0 whose min is the value
-			H[pl] = 15u;
-			RA[pl] = qo + 16u * (uint32_t)r;
-			MA[pl] = 0u;
-			MK[pl] = 0u;
-			uint32_t c = live ? 256u : 0u;
-			if (live && kind == (uint32_t)KIND_SAME) {
-				H[pl] = 0u;
-				MA[pl] = qo;
-				c = 1u;
-			}
-			else if (live && kind > (uint32_t)KIND_NORMAL_RLE) {
-				bad = true;
-				H[pl] = 0u;
-				c = 0u;
-			}
-			if (__any_sync(FULL, normal)) {
-				coded |= 1u << pl;
-				const uint8_t* q = p + qo;
-				const uint32_t h = normal ? ((uint32_t)(q[r >> 1] >> (4 * (r & 1))) & 15u) : 15u;
-				const bool nomin = (0x80C0u >> h) & 1u; // headers 6, 7, 15 carry no min
-				const bool is_rle = normal && (h | 1u) == 7u;
-				// mins: one byte per row that uses one, or RLE coded (all 16) when the plane kind says so (:2071-2084)
-				uint32_t mins_len, min_at = 0;
-				const uint32_t nmb = (__ballot_sync(FULL, normal && !nomin) >> hsh) & 0xFFFFu;
-				if (kind == (uint32_t)KIND_NORMAL_RLE && normal) {
-					const uint32_t nonrep = ~rd16(q + 8) & 0xFFFFu;
-					mins_len = 2u + __popc(nonrep);
-					const uint32_t cnt = __popc(nonrep & ((2u << r) - 1u));
-					min_at = cnt ? qo + 8u + 2u + cnt - 1u : 0u;
-				}
-				else {
-					mins_len = __popc(nmb);
-					if (normal && !nomin)
-						min_at = qo + 8u + __popc(nmb & below);
-				}
-				// row payload offsets: a scan over the 16 rows; RLE rows (2 + number of non repeats) resolved in row order
-				const uint32_t pay = !normal ? 0u : (h == 15u ? 16u : (is_rle ? 0u : 2u * (h & 7u)));
-				uint32_t incl = pay;
-#pragma unroll
-				for (int d = 1; d < 16; d <<= 1) {
-					const uint32_t t = __shfl_up_sync(FULL, incl, d, 16);
-					if (r >= d)
-						incl += t;
-				}
-				uint32_t rowoff = incl - pay;
-				uint32_t consumed = __shfl_sync(FULL, incl, 15, 16);
-				uint32_t mask16 = 0;
-				uint32_t rle_rows = (__ballot_sync(FULL, is_rle) >> hsh) & 0xFFFFu;
-				if (__any_sync(FULL, rle_rows != 0u)) {
-					const uint8_t* rows = q + 8u + mins_len;
-					uint32_t acc = 0, extra = 0;
-					while (__any_sync(FULL, rle_rows != 0u)) {
-						const bool on = rle_rows != 0u;
-						const int L = on ? (__ffs((int)rle_rows) - 1) : 0;
-						rle_rows &= rle_rows - 1u;
-						const uint32_t at = __shfl_sync(FULL, rowoff, L, 16) + acc;
-						if (on) {
-							const uint32_t m = rd16(rows + at);
-							const uint32_t psz = 2u + __popc(~m & 0xFFFFu);
-							if (r == L)
-								mask16 = m;
-							if (r > L)
-								extra += psz;
-							acc += psz;
-						}
-					}
-					rowoff += extra;
-					consumed += acc;
-				}
-				if (normal) {
-					H[pl] = h;
-					RA[pl] = qo + 8u + mins_len + rowoff + (is_rle ? 2u : 0u);
-					MA[pl] = min_at;
-					MK[pl] = mask16;
-					c = 8u + mins_len + consumed;
-				}
-			}
-			qo += c;
-		}
-
-		// ---- ROWS: loads first (independent of one another), then the planes
-		uint32_t O[T][4];  // the row's 16 bytes; for rows that end in a prefix sum: the 16 summands (without the min)
-		uint32_t MIN[T];
-#pragma unroll
-		for (int pl = 0; pl < T; ++pl) {
-			const uint32_t h = H[pl];
-			O[pl][0] = O[pl][1] = O[pl][2] = O[pl][3] = 0u;
-			MIN[pl] = 0u;
-			if (live && (h & 7u) != 0u) // every header but 0 and 8 has a payload (6, 7: the non repeated bytes after the mask)
-				load16_unaligned(p + RA[pl], O[pl]);
-			if (live && MA[pl] != 0u)
-				MIN[pl] = p[MA[pl]];
-		}
-		uint32_t Z[T]; // c | a << 8 | lead << 16 | is_sum << 24
-#pragma unroll
-		for (int pl = 0; pl < T; ++pl) {
-			const uint32_t h = H[pl], bits = h & 7u, minv = MIN[pl], mask16 = MK[pl];
-			uint32_t (&v)[4] = O[pl];
-			if (!((coded >> pl) & 1u)) {
-				// ALL_SAME / RAW in both halves: no row depends on another, nothing to unpack
-				if (h == 0u)
-					v[0] = v[1] = v[2] = v[3] = splat(minv);
-				Z[pl] = 0u;
-				continue;
-			}
-			uint32_t a = 0, c = 0, lead = 0;
-			bool is_sum = false;
-			if (!live) {
-				v[0] = v[1] = v[2] = v[3] = 0u;
-			}
-			else if (h == 15u) { // raw row
-				c = v[3] >> 24;
-			}
-			else if ((h | 1u) == 7u) {
-				// [mask:2][non repeated bytes] (decode_rle_flat, :1939-1968); header 6: the bytes are deltas and the row
-				// restarts from delta 0 (:1982)
-				uint32_t x0, x1, x2, x3, lead_lo, lead_hi, s0, s1;
-				rle_expand8(mask16 & 0xFFu, v[0], v[1], x0, x1, lead_lo);
-				window8(v, __popc(~mask16 & 0xFFu), s0, s1);
-				rle_expand8(mask16 >> 8, s0, s1, x2, x3, lead_hi);
-				if (h == 6u || lead_lo < 8u)
-					fill_lead8(x2, x3, lead_hi, x1 >> 24);
-				v[0] = x0;
-				v[1] = x1;
-				v[2] = x2;
-				v[3] = x3;
-				if (h == 6u)
-					is_sum = true;
-				else {
-					lead = lead_lo < 8u ? lead_lo : 8u + lead_hi;
-					a = lead == 16u;
-					c = a ? 0u : (x3 >> 24);
-				}
-			}
-			else {
-				// bit packed: two groups of 8 values, `bits` bytes each (:1451-1486); header >= 8: deltas
-				uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-				if (bits) {
-					const uint32_t s = 8u - bits;
-					const uint32_t P1 = 1u << s, P2 = P1 * P1, m4 = (0xFFu >> s) * 0x01010101u;
-					const bool up = bits >= 4u;
-					const uint32_t y0 = up ? v[1] : v[0], y1 = up ? v[2] : v[1], y2 = up ? v[3] : v[2];
-					const uint32_t sh = (bits & 3u) * 8u;
-					const uint32_t g1l = __funnelshift_r(y0, y1, sh), g1h = __funnelshift_r(y1, y2, sh);
-					x0 = unpack4f(v[0], P2, P1, m4);
-					x1 = unpack4f(__funnelshift_r(v[0], v[1], 4u * bits), P2, P1, m4);
-					x2 = unpack4f(g1l, P2, P1, m4);
-					x3 = unpack4f(__funnelshift_r(g1l, g1h, 4u * bits), P2, P1, m4);
-				}
-				if (h >= 8u) {
-					is_sum = true;
-					v[0] = x0;
-					v[1] = x1;
-					v[2] = x2;
-					v[3] = x3;
-				}
-				else {
-					// value = packed + min per byte; packed < 64, so adding the low 7 bits of the min cannot carry
-					const uint32_t m4v = splat(minv);
-					const uint32_t m7 = m4v & 0x7F7F7F7Fu, mh = m4v & 0x80808080u;
-					v[0] = (x0 + m7) ^ mh;
-					v[1] = (x1 + m7) ^ mh;
-					v[2] = (x2 + m7) ^ mh;
-					v[3] = (x3 + m7) ^ mh;
-					c = v[3] >> 24;
-				}
-			}
-			if (is_sum) {
-				// the row's total: its affine map is last = prev + total (delta-RLE rows have no min: minv is 0 for them)
-				uint32_t tot = 16u * ((h | 1u) == 7u ? 0u : minv);
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					tot = sad4_acc(v[j], 0u, tot);
-				a = 1;
-				c = tot & 0xFFu;
-			}
-			Z[pl] = (c & 0xFFu) | (a << 8) | (lead << 16) | ((is_sum ? 1u : 0u) << 24);
-		}
-		// ---- carries across the rows of the block: inclusive scan of the affine maps, shifted by one row; two planes per scan
-#pragma unroll
-		for (int pp = 0; pp < T; pp += 2) {
-			uint32_t carry2 = 0;
-			const uint32_t need = (Z[pp] | Z[pp + 1]) & 0x00FF0100u; // some a or lead set
-			if (__any_sync(FULL, need != 0u)) {
-				uint32_t z = (Z[pp] & 0x1FFu) | ((Z[pp + 1] & 0x1FFu) << 16);
-#pragma unroll
-				for (int d = 1; d < 16; d <<= 1) {
-					const uint32_t y = __shfl_up_sync(FULL, z, d, 16);
-					if (r >= d)
-						z = compose_maps2(z, y);
-				}
-				carry2 = __shfl_up_sync(FULL, z, 1, 16) & 0x00FF00FFu;
-				if (r == 0)
-					carry2 = 0; // the byte before the block is 0
-			}
-#pragma unroll
-			for (int k = 0; k < 2; ++k) {
-				const int pl = pp + k;
-				const uint32_t carry = (carry2 >> (16 * k)) & 0xFFu;
-				const uint32_t lead = (Z[pl] >> 16) & 0xFFu;
-				if (Z[pl] >> 24) {
-					uint32_t x[4] = { O[pl][0], O[pl][1], O[pl][2], O[pl][3] };
-					prefix16(x, (H[pl] | 1u) == 7u ? 0u : MIN[pl], carry, O[pl]);
-				}
-				else if (lead)
-					fill_lead16(O[pl], lead, carry);
-			}
-		}
-		if (live && !bad)
-			store_row_planes<T>(out, r, O);
-		return bad ? 0xFFFFFFFFu : qo;
-	}
-
-#endif
 	// Two superblocks per warp: the lanes of half h decode the superblock [code][csize:3][payload] at offset `at`
 	// (of that half) into dsize bytes at `out`.  valid: the half has a superblock.  Returns the half's device error bits.
 	template<int T>

@@ -243,25 +243,6 @@ def test_pipelined_host_path_matches_single_launch(monkeypatch):
         assert run(api.decompress, got, T, raw.size) == raw.tobytes()
 
 
-def test_split_decoder_matches(monkeypatch):
-    """The opt-in parser/decoder split (sb_decode_split.cuh: scalar threads walk the block streams, half-warps decode
-    single blocks behind them) decodes the same bytes as the default decoder, incl. LZ blocks, COPY superblocks,
-    partial tails and corrupt input."""
-    monkeypatch.setenv("STENOS_B200_SPLIT_DECODER", "1")
-    rng = np.random.default_rng(21)
-    for T in (2, 4, 8):
-        parts = [raw_of(dists.make(name, 131072 // T + 77, T, seed=3)) for name in ("ramp_noise16", "random", "lz_pairs", "const", "sparse_changes")]
-        raw = np.concatenate(parts)
-        raw = raw[: raw.size - raw.size % T]
-        c = port.compress(raw, T)
-        assert run(api.decompress, c, T, raw.size) == raw.tobytes()
-        bad = bytearray(c)
-        for i in rng.integers(12, len(bad), 40):
-            bad[i] ^= 0x5A
-        r = run(api.decompress, bytes(bad), T, raw.size)  # an error string or bytes, never a crash
-        assert isinstance(r, (bytes, str))
-
-
 def test_flow_encoder_spill_path_with_minimum_rings(monkeypatch):
     """The fast encoder (sb_flow.cuh) with its staging rings at the smallest legal size: pieces whose superblock is not
     placed yet move to HBM spill slots all the time.  Streams must not change."""

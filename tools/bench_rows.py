@@ -251,6 +251,8 @@ def main():
         for T, name in ((2, "int16_sine"), (4, "float32_sensor"), (8, "float64_sensor")):
             for chunk in (131072, 262144, 524288):
                 print(json.dumps(row_filters(T, name, args.filter_mib << 20, chunk, dev, pk)), flush=True)
+    if "filters8" in rows:  # profiling: the T = 8 filters alone
+        print(json.dumps(row_filters(8, "float64_sensor", args.filter_mib << 20, 262144, dev, pk)), flush=True)
     if "gather" in rows:
         print(json.dumps(row_gather(nbytes, 1 << 20, dev, pk)), flush=True)
     if "buckets" in rows:

@@ -40,13 +40,6 @@ def main():
     t_f = timeit(lambda: ctx.decompress_async(d_dst, T, c, d_out, nbytes, nbytes, d_res, None))
     if not os.environ.get("NOCHECK"):
         assert torch.equal(d_out, d_src)
-    if os.environ.get("SPLITMODES"):
-        os.environ["STENOS_B200_SPLIT_MODE"] = "2"
-        t2 = timeit(lambda: ctx.decompress_async(d_dst, T, c, d_out, nbytes, nbytes, d_res, d_off))
-        os.environ["STENOS_B200_SPLIT_MODE"] = "1"
-        t1 = timeit(lambda: ctx.decompress_async(d_dst, T, c, d_out, nbytes, nbytes, d_res, d_off))
-        os.environ["STENOS_B200_SPLIT_MODE"] = "0"
-        print("split decoder: parse only %.3f ms | decode only %.3f ms" % (t1, t2))
     print("bytes %d csize %d | compress %.3f ms | index %.3f ms (accepted=%d) | decode(with index) %.3f ms | decode(full) %.3f ms" % (nbytes, c, t_c, t_i, acc, t_d, t_f))
 
 main()
