@@ -365,6 +365,46 @@ def test_unchanged_cvector_header_is_a_drop_in(tmp_path):
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+# ------------------------------------------------------------------------------------------------
+# round 2
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,name", [(2, "int16_sine"), (8, "int64_ramp_runs")])
+def test_full_size_sampled_superblocks_other_element_sizes(T, name):
+    """BASELINE.json configs at 1 GiB for the element sizes the headline does not cover: device resident round trip,
+    the frame header, the superblock index, and sampled superblocks byte for byte against the oracle."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    nbytes = 1 << 30
+    d_src = synth.make_torch(name, nbytes // T, device=dev).view(torch.uint8)
+    ctx = api.Context(stream=torch.cuda.current_stream())
+    cap = api.bound(nbytes) + (1 << 20)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(2, dtype=torch.int64, device=dev)
+    n_sb = nbytes // 131072
+    d_off = torch.zeros(n_sb + 1, dtype=torch.int64, device=dev)
+    ctx.compress_async(d_src, T, nbytes, d_dst, cap, d_res, d_off)
+    torch.cuda.synchronize()
+    total, err = (int(x) for x in d_res.cpu().numpy())
+    assert err == 0
+    offs = d_off.cpu().numpy()
+    assert offs[0] == 8 and offs[-1] == total and np.all(np.diff(offs) > 4)
+    assert d_dst[:8].cpu().numpy().tobytes() == bytes([0]) + int(nbytes).to_bytes(7, "little")
+    rng = np.random.default_rng(T)
+    for s in [0, 1, n_sb - 1] + list(rng.integers(0, n_sb, 29)):
+        s = int(s)
+        raw = d_src[s * 131072:(s + 1) * 131072].cpu().numpy()
+        got = d_dst[int(offs[s]): int(offs[s + 1])].cpu().numpy().tobytes()
+        assert got == port.compress_superblock(raw, T, room=1 << 20), s
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    for index in (d_off, None):  # with the encoder's index, and walking the headers on the device
+        d_out.zero_()
+        ctx.decompress_async(d_dst, T, total, d_out, nbytes, nbytes, d_res, index)
+        torch.cuda.synchronize()
+        assert d_res.cpu().numpy()[1] == 0
+        assert torch.equal(d_out, d_src)
+
+
 def test_decoder_accepts_raw_block_marker_252():
     """Blocks stored raw behind marker 252 only appear in time limited streams of the reference (block_compress.h:2118-2123),
     which this encoder never writes; the decoder must read them.  Hand-built streams, checked against the oracle's decoder."""
