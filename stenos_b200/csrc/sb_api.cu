@@ -333,7 +333,11 @@ namespace
 {
 	using namespace sb;
 
-	bool supported_T(size_t T) { return T == 2 || T == 4 || T == 8; }
+	bool supported_T(size_t T) { return T == 2 || T == 4 || T == 8; } // the fast kernels, the device-resident API, filters, buckets
+	// other element sizes (first slice): 3 and 6 bytes -- no LZ at these sizes (block_compress.h:1210: T % 4 == 0
+	// only) -- through the generic kernels (encode_frame_kernel / decode_frame_kernel: one warp per block, lane per half row)
+	bool generic_T(size_t T) { return T == 3 || T == 6; }
+	bool device_T(size_t T) { return supported_T(T) || generic_T(T); }
 
 #ifndef ENCODE_THREADS_2
 #define ENCODE_THREADS_2 1024
@@ -476,7 +480,7 @@ namespace
 	size_t launch_encode(stenos_context* ctx, size_t T, EncodeParams P)
 	{
 		uint32_t n_stream = 0;
-		if (P.level != 0 && !ctx->legacy_encoder) {
+		if (P.level != 0 && !ctx->legacy_encoder && supported_T(T)) {
 			const uint64_t block = T * 256, hs = (T + 1) / 2;
 			const uint64_t need = (P.sb_bytes / block) * (block + hs) + 8 * T + 32 + 8 * T + block; // worst stream + slack (+ a partial block's worst case)
 			const uint64_t first_off = P.header_len ? (uint64_t)P.header_len : P.base_offset;
@@ -503,6 +507,8 @@ namespace
 			case 2: return launch_encode_T<2, ENCODE_THREADS_2>(ctx, P);
 			case 4: return launch_encode_T<4, ENCODE_THREADS_4>(ctx, P);
 			case 8: return launch_encode_T<8, ENCODE_THREADS_8>(ctx, P);
+			case 3: return launch_encode_T<3, 512>(ctx, P);
+			case 6: return launch_encode_T<6, 512>(ctx, P);
 		}
 		return STENOS_ERROR_INVALID_PARAMETER;
 	}
@@ -541,6 +547,14 @@ namespace
 		++g_launches;
 		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
 	}
+	template<int T>
+	size_t launch_decode_generic_T(stenos_context* ctx, const DecodeParams& P)
+	{
+		const unsigned grid = (P.n_sb + DECODE_WARPS - 1) / DECODE_WARPS;
+		STENOS_LAUNCH(decode_frame_kernel<T>, dim3(grid), dim3(DECODE_WARPS * 32), DECODE_WARPS * 512, ctx->stream(), P);
+		++g_launches;
+		return cudaGetLastError() == cudaSuccess ? 0 : STENOS_ERROR_UNDEFINED;
+	}
 	size_t launch_decode(stenos_context* ctx, size_t T, const DecodeParams& P)
 	{
 		if (!P.n_sb)
@@ -549,6 +563,8 @@ namespace
 			case 2: return launch_decode_T<2>(ctx, P);
 			case 4: return launch_decode_T<4>(ctx, P);
 			case 8: return launch_decode_T<8>(ctx, P);
+			case 3: return launch_decode_generic_T<3>(ctx, P);
+			case 6: return launch_decode_generic_T<6>(ctx, P);
 		}
 		return STENOS_ERROR_INVALID_PARAMETER;
 	}
@@ -753,7 +769,7 @@ namespace
 		if (ctx->max_ns != 0)
 			return STENOS_ERROR_INVALID_PARAMETER; // time limited compression is wall-clock driven: out of scope
 		const int level = ctx->level;
-		if (level > 1 || !supported_T(T))
+		if (level > 1 || !device_T(T))
 			return STENOS_ERROR_INVALID_PARAMETER; // no CPU fallback: levels >= 2 need Zstd
 		if (sb > STENOS_BLOCK_SIZE)
 			return STENOS_ERROR_INVALID_PARAMETER; // shared-memory slots hold at most 128 KiB superblocks
@@ -1081,7 +1097,7 @@ namespace
 			if (total == 0)
 				return 0;
 		}
-		if (!supported_T(T))
+		if (!device_T(T))
 			return STENOS_ERROR_INVALID_PARAMETER;
 		const size_t n_sb = (size_t)((total + sb - 1) / sb);
 		if (n_sb > 0xFFFFFFF0ull)
@@ -1330,7 +1346,7 @@ namespace
 	// then looked at again by the hybrid path (which returns that error if it finds no Zstd superblock either).
 	size_t decompress_impl(stenos_context* ctx, const void* src_, size_t T, size_t size, void* dst_, size_t dst_size, bool frame, size_t bare_sb)
 	{
-		if (!frame || !supported_T(T) || size < 13)
+		if (!frame || !supported_T(T) || size < 13) // (hybrid frames: T in {2,4,8}; the generic sizes decode level 0 / 1 frames)
 			return decompress_level1(ctx, src_, T, size, dst_, dst_size, frame, bare_sb);
 		if (!ctx->activate())
 			return STENOS_ERROR_ALLOC;
@@ -1960,9 +1976,9 @@ namespace
 						FilterParams F = P;
 						F.bytes = fused_chunks * chunk;
 						switch (T) {
-							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
-							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
-							case 8: STENOS_LAUNCH(unshuffle_delta_kernel<8>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256, st, F); break;
+							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 2 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
+							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 4 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
+							case 8: STENOS_LAUNCH(unshuffle_delta_kernel<8>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 8 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
 						}
 						++g_launches;
 					}

@@ -163,6 +163,10 @@ namespace sb
 		p3 = __byte_perm(t2, t3, 0x7632);
 	}
 
+	// byte i of the 8 * T bytes a lane holds in w[0 .. 2T)
+	template<int T>
+	__device__ __forceinline__ uint32_t lane_byte(const uint32_t (&w)[2 * T], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
 	// Lane-local view of one 256-element block: lane l owns elements 8l..8l+7, i.e. for every byte
 	// plane p the 8 bytes lo[p] (elements 0..3) and hi[p] (elements 4..7).  W = 2*T input words.
 	template<int T>
@@ -178,11 +182,25 @@ namespace sb
 			transpose4(w[0], w[1], w[2], w[3], lo[0], lo[1], lo[2], lo[3]);
 			transpose4(w[4], w[5], w[6], w[7], hi[0], hi[1], hi[2], hi[3]);
 		}
-		else { // T == 8
+		else if (T == 8) {
 			transpose4(w[0], w[2], w[4], w[6], lo[0], lo[1], lo[2], lo[3]);
 			transpose4(w[1], w[3], w[5], w[7], lo[4], lo[5], lo[6], lo[7]);
 			transpose4(w[8], w[10], w[12], w[14], hi[0], hi[1], hi[2], hi[3]);
 			transpose4(w[9], w[11], w[13], w[15], hi[4], hi[5], hi[6], hi[7]);
+		}
+		else {
+			// any other element size (3, 6: SURVEY 8 f3): byte p of element j is byte j * T + p of the lane's 8 * T bytes
+#pragma unroll
+			for (int p = 0; p < T; ++p) {
+				uint32_t l = 0, h = 0;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					l |= lane_byte<T>(w, j * T + p) << (8 * j);
+					h |= lane_byte<T>(w, (4 + j) * T + p) << (8 * j);
+				}
+				lo[p] = l;
+				hi[p] = h;
+			}
 		}
 	}
 	template<int T>
@@ -199,11 +217,23 @@ namespace sb
 			transpose4(lo[0], lo[1], lo[2], lo[3], w[0], w[1], w[2], w[3]);
 			transpose4(hi[0], hi[1], hi[2], hi[3], w[4], w[5], w[6], w[7]);
 		}
-		else {
+		else if (T == 8) {
 			transpose4(lo[0], lo[1], lo[2], lo[3], w[0], w[2], w[4], w[6]);
 			transpose4(lo[4], lo[5], lo[6], lo[7], w[1], w[3], w[5], w[7]);
 			transpose4(hi[0], hi[1], hi[2], hi[3], w[8], w[10], w[12], w[14]);
 			transpose4(hi[4], hi[5], hi[6], hi[7], w[9], w[11], w[13], w[15]);
+		}
+		else {
+#pragma unroll
+			for (int i = 0; i < 2 * T; ++i) {
+				uint32_t v = 0;
+#pragma unroll
+				for (int b = 0; b < 4; ++b) {
+					const int idx = 4 * i + b, j = idx / T, p = idx % T; // byte p of element j
+					v |= (((j < 4 ? lo[p] : hi[p]) >> (8 * (j & 3))) & 0xFFu) << (8 * b);
+				}
+				w[i] = v;
+			}
 		}
 	}
 
@@ -211,6 +241,17 @@ namespace sb
 	template<int T>
 	__device__ __forceinline__ void load_lane_words(const uint8_t* __restrict__ block, int lane, uint32_t (&w)[2 * T])
 	{
+		if (T % 2 != 0 || ((8 * T) % 16) != 0) {
+			// 8 * T bytes per lane that are not a multiple of 16: 8-byte loads (the lane's bytes start 8-byte aligned)
+			const uint2* q = reinterpret_cast<const uint2*>(block + (size_t)lane * 8 * T);
+#pragma unroll
+			for (int i = 0; i < T; ++i) {
+				const uint2 v = q[i];
+				w[2 * i] = v.x;
+				w[2 * i + 1] = v.y;
+			}
+			return;
+		}
 		const uint4* p = reinterpret_cast<const uint4*>(block + (size_t)lane * 8 * T);
 #pragma unroll
 		for (int i = 0; i < T / 2; ++i) {
@@ -224,6 +265,13 @@ namespace sb
 	template<int T>
 	__device__ __forceinline__ void store_lane_words(uint8_t* __restrict__ block, int lane, const uint32_t (&w)[2 * T])
 	{
+		if (T % 2 != 0 || ((8 * T) % 16) != 0) {
+			uint2* q = reinterpret_cast<uint2*>(block + (size_t)lane * 8 * T);
+#pragma unroll
+			for (int i = 0; i < T; ++i)
+				q[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+			return;
+		}
 		uint4* p = reinterpret_cast<uint4*>(block + (size_t)lane * 8 * T);
 #pragma unroll
 		for (int i = 0; i < T / 2; ++i)

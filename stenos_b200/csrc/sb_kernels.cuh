@@ -210,6 +210,21 @@ namespace sb
 			bool err = false;
 			if (P.level == 0) {
 			}
+			else if (!exact && !(T == 2 || T == 4 || T == 8)) {
+				// other element sizes: one warp per block, one lane per half row (sb_encode.cuh)
+				for (uint32_t b = warp; b < nfull; b += nwarps) {
+					bool e = false;
+					const uint32_t sz = encode_block<T, false>(in + (size_t)b * L::BLOCK, smem + b * L::STRIDE, lz_scratch, lane, 0xFFFFFFFFu, e);
+					if (lane == 0)
+						sizes[b] = sz;
+				}
+				if (rem && warp == (int)(nfull % nwarps)) {
+					bool e = false;
+					const uint32_t sz = encode_partial_block<T, false>(in + (size_t)nfull * L::BLOCK, rem, smem + nfull * L::STRIDE, lane, 0xFFFFFFFFu, e);
+					if (lane == 0)
+						sizes[nfull] = sz;
+				}
+			}
 			else if (!exact) {
 				// full blocks in pairs: one warp per pair, one lane per 16-element row (sb_encode_rows.cuh)
 				const uint32_t npairs = (nfull + 1u) >> 1;

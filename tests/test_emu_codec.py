@@ -31,7 +31,7 @@ def run(fn, *a, **k):
         return {"-6": "DST_OVERFLOW", "-2": "SRC_OVERFLOW", "-4": "INVALID_INPUT"}.get(str(e).split()[-1], str(e))
 
 
-@pytest.mark.parametrize("T", [2, 4, 8])
+@pytest.mark.parametrize("T", [2, 4, 8, 3, 6])  # 3 and 6: the generic kernels
 def test_frames_match_oracle(T):
     for name in dists.names():
         for n in (256, 700, 33):
@@ -78,7 +78,7 @@ def test_level0_and_unsupported_parameters():
     assert api.compress(raw, 4, level=0) == port.compress(raw, 4, level=0)
     assert api.decompress(port.compress(raw, 4, level=0), 4, raw.size) == raw.tobytes()
     assert run(api.compress, raw, 4, level=2) == "INVALID_PARAMETER"  # Zstd levels: no CPU fallback
-    assert run(api.compress, raw[:39999], 3) == "INVALID_PARAMETER"
+    assert run(api.compress, raw[:40000], 5) == "INVALID_PARAMETER"  # element sizes other than 2, 4, 8, 3, 6 are not built
     assert run(api.compress, raw, 0) == "INVALID_BYTESOFTYPE"
     ctx = api.Context()
     ctx.set_max_nanoseconds(1000)
@@ -87,7 +87,7 @@ def test_level0_and_unsupported_parameters():
 
 def test_room_dependent_decisions():
     ctx = api.Context()
-    for T in (4, 8):
+    for T in (4, 8, 3):
         for name in ("random", "lz_pairs", "repeat_period7", "sorted", "mostly_random_some_repeats"):
             raw = raw_of(dists.make(name, 256, T, seed=1))
             for room in (T * 256 + 16, T * 256 + 4, T * 256 + 64, T * 256 + 300):
@@ -361,3 +361,22 @@ def test_forced_strategy_frames_equal_the_reference_where_it_picks_that_strategy
     assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 1, 4) == "INVALID_PARAMETER"
     assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 3, 5) == "INVALID_PARAMETER"
     assert run(ctx.compress_strategy, raw_of(np.arange(100000, dtype=np.int32)), 4, 3, 4, 100) == "DST_OVERFLOW"
+
+
+@pytest.mark.parametrize("T", [3, 6])
+def test_other_element_sizes_multi_superblock(T):
+    """Element sizes 3 and 6 (first slice): superblocks of 130560 bytes (stenos.cpp:71-76), partial tail blocks, the
+    < 128 byte Zstd tail, COPY superblocks -- frames identical to the oracle's, round trips, corrupt input rejected."""
+    ctx = api.Context()
+    sb = (131072 // (256 * T)) * 256 * T
+    for name, n in (("ramp_noise16", sb // T + 300), ("random", sb // T + 5)):  # (the GPU fuzz test has the breadth; the emulator is slow)
+        raw = raw_of(dists.make(name, n, T, seed=3))
+        want = port.compress(raw, T)
+        assert ctx.compress(raw, T) == want, (name, n)
+        assert ctx.decompress(np.frombuffer(want, dtype=np.uint8), T, raw.size) == raw.tobytes(), (name, n)
+        for ds in (len(want) - 1,):
+            assert run(ctx.compress, raw, T, dst_size=ds) == run(port.compress, raw, T, dst_size=ds), (name, ds)
+    bad = bytearray(port.compress(raw_of(dists.make("ramp_noise16", 3000, T, seed=4)), T))
+    bad[8] = 9
+    assert run(ctx.decompress, bytes(bad), T, 3000 * T) == "INVALID_INPUT"
+    assert run(ctx.compress, raw_of(np.arange(500, dtype=np.uint8)), 5) == "INVALID_PARAMETER"
