@@ -1,5 +1,5 @@
 #!/bin/bash
-# variants of the library timed with tools/time_parts.py: gpu_r2c.sh <tag> <T list> <variant names ...> ("main" = the in-tree library)
+# variants of the library timed with tools/time_parts.py: gpu_variants.sh <tag> <T list> <variant names ...> ("main" = the in-tree library)
 TAG=$1; TS=$2; shift 2; mkdir -p gpurun_out
 for V in "$@"; do
   for T in $TS; do
