@@ -11,7 +11,7 @@
  * entry points that work on device-resident buffers without host synchronisation.
  *
  * Domain of the device path: compression levels 0 and 1, no time limit; element sizes 2, 4 and 8 bytes (the fast
- * kernels, every entry point) and 3 and 6 bytes (generic kernels, the stenos_compress / stenos_decompress family only).
+ * kernels, every entry point) and 3, 5, 6 and 7 bytes (generic kernels, the stenos_compress / stenos_decompress family only).
  * Decompression also reads the frames the reference writes at levels 2..9 (element sizes 2, 4, 8: Zstd on the host,
  * the rest on the device).  Anything else returns STENOS_ERROR_INVALID_PARAMETER -- there is no CPU fallback.
  * src / dst may be host pointers (pageable or pinned) or device pointers; they are detected.

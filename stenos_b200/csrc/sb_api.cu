@@ -334,9 +334,9 @@ namespace
 	using namespace sb;
 
 	bool supported_T(size_t T) { return T == 2 || T == 4 || T == 8; } // the fast kernels, the device-resident API, filters, buckets
-	// other element sizes (first slice): 3 and 6 bytes -- no LZ at these sizes (block_compress.h:1210: T % 4 == 0
+	// other element sizes (first slice): 3, 5, 6 and 7 bytes -- no LZ at these sizes (block_compress.h:1210: T % 4 == 0
 	// only) -- through the generic kernels (encode_frame_kernel / decode_frame_kernel: one warp per block, lane per half row)
-	bool generic_T(size_t T) { return T == 3 || T == 6; }
+	bool generic_T(size_t T) { return T == 3 || T == 5 || T == 6 || T == 7; }
 	bool device_T(size_t T) { return supported_T(T) || generic_T(T); }
 
 #ifndef ENCODE_THREADS_2
@@ -508,7 +508,9 @@ namespace
 			case 4: return launch_encode_T<4, ENCODE_THREADS_4>(ctx, P);
 			case 8: return launch_encode_T<8, ENCODE_THREADS_8>(ctx, P);
 			case 3: return launch_encode_T<3, 512>(ctx, P);
+			case 5: return launch_encode_T<5, 512>(ctx, P);
 			case 6: return launch_encode_T<6, 512>(ctx, P);
+			case 7: return launch_encode_T<7, 512>(ctx, P);
 		}
 		return STENOS_ERROR_INVALID_PARAMETER;
 	}
@@ -564,7 +566,9 @@ namespace
 			case 4: return launch_decode_T<4>(ctx, P);
 			case 8: return launch_decode_T<8>(ctx, P);
 			case 3: return launch_decode_generic_T<3>(ctx, P);
+			case 5: return launch_decode_generic_T<5>(ctx, P);
 			case 6: return launch_decode_generic_T<6>(ctx, P);
+			case 7: return launch_decode_generic_T<7>(ctx, P);
 		}
 		return STENOS_ERROR_INVALID_PARAMETER;
 	}

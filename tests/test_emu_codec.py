@@ -31,7 +31,7 @@ def run(fn, *a, **k):
         return {"-6": "DST_OVERFLOW", "-2": "SRC_OVERFLOW", "-4": "INVALID_INPUT"}.get(str(e).split()[-1], str(e))
 
 
-@pytest.mark.parametrize("T", [2, 4, 8, 3, 6])  # 3 and 6: the generic kernels
+@pytest.mark.parametrize("T", [2, 4, 8, 3, 5, 6, 7])  # 3, 5, 6, 7: the generic kernels
 def test_frames_match_oracle(T):
     for name in dists.names():
         for n in (256, 700, 33):
@@ -78,7 +78,7 @@ def test_level0_and_unsupported_parameters():
     assert api.compress(raw, 4, level=0) == port.compress(raw, 4, level=0)
     assert api.decompress(port.compress(raw, 4, level=0), 4, raw.size) == raw.tobytes()
     assert run(api.compress, raw, 4, level=2) == "INVALID_PARAMETER"  # Zstd levels: no CPU fallback
-    assert run(api.compress, raw[:40000], 5) == "INVALID_PARAMETER"  # element sizes other than 2, 4, 8, 3, 6 are not built
+    assert run(api.compress, raw[:39996], 9) == "INVALID_PARAMETER"  # element sizes above 8 (and 1) are not built
     assert run(api.compress, raw, 0) == "INVALID_BYTESOFTYPE"
     ctx = api.Context()
     ctx.set_max_nanoseconds(1000)
@@ -379,4 +379,4 @@ def test_other_element_sizes_multi_superblock(T):
     bad = bytearray(port.compress(raw_of(dists.make("ramp_noise16", 3000, T, seed=4)), T))
     bad[8] = 9
     assert run(ctx.decompress, bytes(bad), T, 3000 * T) == "INVALID_INPUT"
-    assert run(ctx.compress, raw_of(np.arange(500, dtype=np.uint8)), 5) == "INVALID_PARAMETER"
+    assert run(ctx.compress, raw_of(np.arange(495, dtype=np.uint8)), 9) == "INVALID_PARAMETER"

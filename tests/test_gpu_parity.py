@@ -96,7 +96,7 @@ def test_golden_filters():
         assert ctx.unshuffle(z[k + "_shuffle_delta"], T, 0, True) == a.tobytes(), k
 
 
-@pytest.mark.parametrize("T", [2, 4, 8, 3, 6])  # 3 and 6: the generic kernels
+@pytest.mark.parametrize("T", [2, 4, 8, 3, 5, 6, 7])  # 3, 5, 6, 7: the generic kernels
 def test_fuzz_vs_oracle(T):
     ctx = api.Context()
     for name in dists.names():
@@ -125,12 +125,12 @@ def test_edge_cases():
     assert api.compress(raw, 8, level=0) == port.compress(raw, 8, level=0)
     assert run(api.compress, raw, 8, level=3) == "INVALID_PARAMETER"
     assert api.compress(raw[:39999], 3) == port.compress(raw[:39999], 3)  # element size 3: the generic kernels
-    assert run(api.compress, raw[:40000], 5) == "INVALID_PARAMETER"  # not built: no CPU fallback
+    assert run(api.compress, raw[:39996], 9) == "INVALID_PARAMETER"  # not built: no CPU fallback
 
 
 def test_room_dependent_decisions():
     ctx = api.Context()
-    for T in (2, 4, 8, 3, 6):
+    for T in (2, 4, 8, 3, 5, 6, 7):
         for name in dists.names():
             raw = raw_of(dists.make(name, 256, T, seed=1))
             for room in (T * 256 + 16, T * 256 + 4, T * 256 + 64):
