@@ -205,6 +205,44 @@ def row_hybrid(name, T, nbytes, level=3, strategy=4):
             "note": "host Zstd bound on both sides; the device part is the filter (rows `filters`)"}
 
 
+def row_generic(T, nbytes, dev, pk):
+    """Element sizes 3, 5, 6, 7: the generic kernels through the synchronous reference-shaped calls on device pointers
+    (one launch each; the call's own synchronisation is inside the time).  Parity: a 4 MiB prefix against the oracle's frame."""
+    import time
+    from oracle import port  # the checker
+    n = nbytes // T
+    i = torch.arange(n, dtype=torch.int64, device=dev)
+    v = 3 * i + (i * 2654435761 % 16)
+    raw = torch.stack([((v >> (8 * k)) & 255).to(torch.uint8) for k in range(T)], dim=1).reshape(-1).contiguous()
+    ctx = api.Context()
+    dst = torch.empty(api.bound(raw.numel()), dtype=torch.uint8, device=dev)
+    out = torch.empty_like(raw)
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return min(ts), r
+
+    ctx.compress_raw(raw, T, raw.numel(), dst, dst.numel())
+    tc, r = best(lambda: ctx.compress_raw(raw, T, raw.numel(), dst, dst.numel()))
+    ctx.decompress_raw(dst, T, r, out, out.numel())
+    td, _ = best(lambda: ctx.decompress_raw(dst, T, r, out, out.numel()))
+    ok = bool(torch.equal(out, raw))
+    m = ((4 << 20) // (256 * T)) * 256 * T + 5 * T
+    small = raw[:m].cpu().numpy()
+    ok = ok and ctx.compress(small, T) == port.compress(small, T)
+    ctx.close()
+    alg = raw.numel() + int(r)
+    return {"row": "codec_generic", "T": T, "bytes": int(raw.numel()), "ratio": raw.numel() / int(r), "algorithmic_bytes": alg, "compress_ms": tc * 1e3,
+            "compress_GBps": raw.numel() / tc / 1e9, "compress_frac": alg / tc / 1e9 / pk, "decompress_ms": td * 1e3, "decompress_GBps": raw.numel() / td / 1e9,
+            "decompress_frac": alg / td / 1e9 / pk, "parity": ok, "note": "encode_frame_kernel / decode_frame_kernel (generic in T), synchronous call on device pointers"}
+
+
 def all_rows(dev, stream, pk, steps=5, warmup=3, codec_bytes=1 << 30, filter_bytes=4 << 30, gather_bytes=1 << 30):
     """Every row; a row that fails is reported as {"row": ..., "error": ...} instead of taking the bench line down with it."""
     jobs = []
@@ -215,6 +253,8 @@ def all_rows(dev, stream, pk, steps=5, warmup=3, codec_bytes=1 << 30, filter_byt
     jobs.append(("gather", lambda: row_gather(gather_bytes, 1 << 20, dev, pk, steps, warmup)))
     jobs.append(("bucket_encode", lambda: row_buckets(gather_bytes, dev, pk, steps, warmup)))
     jobs.append(("hybrid_level3", lambda: row_hybrid("float64_sensor", 8, 64 << 20)))
+    for T in (3, 6):
+        jobs.append(("codec_generic", lambda T=T: row_generic(T, 512 << 20, dev, pk)))
     rows = []
     with torch.cuda.stream(stream):
         for name, job in jobs:
@@ -237,7 +277,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, default=1024)
     ap.add_argument("--filter-mib", type=int, default=1024)
-    ap.add_argument("--rows", default="codec,filters,gather,buckets,hybrid")
+    ap.add_argument("--rows", default="codec,filters,gather,buckets,hybrid,generic")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
@@ -257,6 +297,9 @@ def main():
         print(json.dumps(row_gather(nbytes, 1 << 20, dev, pk)), flush=True)
     if "buckets" in rows:
         print(json.dumps(row_buckets(nbytes, dev, pk)), flush=True)
+    if "generic" in rows:
+        for T in (3, 5, 6, 7):
+            print(json.dumps(row_generic(T, 512 << 20, dev, pk)), flush=True)
     if "hybrid" in rows:
         for name, T in (("float64_sensor", 8), ("int16_sine", 2)):
             print(json.dumps(row_hybrid(name, T, 256 << 20)), flush=True)
