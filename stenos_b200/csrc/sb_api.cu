@@ -381,17 +381,18 @@ namespace
 	{
 		const bool one_block = P.sb_bytes <= (uint32_t)T * 256u;
 		if (one_block) {
-			const uint32_t smem = EncodeLayout<T, 1>::smem_bytes(1);
-			int per_sm = 8;
+			// two buckets per warp: the lane-per-row pair encoder, the room-exact one only where the room could matter
+			const uint32_t smem = BUCKET_WARPS * (2u * EncodeLayout<T, 1>::STRIDE + EncodeLayout<T, 1>::LZ_STRIDE);
+			int per_sm = 4;
 #ifndef STENOS_EMU
-			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_frame_kernel<T, 32, 1>, 32, smem) != cudaSuccess || per_sm < 1) {
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_bucket_pairs_kernel<T>, BUCKET_WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
 				cudaGetLastError();
-				per_sm = 8;
+				per_sm = 4;
 			}
 #endif
-			const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(P.n_sb, (long long)ctx->sm_count * per_sm));
-			auto kern = encode_frame_kernel<T, 32, 1>;
-			STENOS_LAUNCH(kern, dim3(grid), dim3(32), smem, ctx->stream(), P);
+			const long long need = ((long long)(P.n_sb + 1) / 2 + BUCKET_WARPS - 1) / BUCKET_WARPS;
+			const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(need, (long long)ctx->sm_count * per_sm));
+			STENOS_LAUNCH(encode_bucket_pairs_kernel<T>, dim3(grid), dim3(BUCKET_WARPS * 32), smem, ctx->stream(), P);
 		}
 		else {
 			constexpr int NT = 256;

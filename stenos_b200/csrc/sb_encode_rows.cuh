@@ -214,13 +214,15 @@ namespace sb
 	// ------------------------------------------------------------------------------------------
 	template<int T, class Place>
 	__device__ __forceinline__ uint32_t encode_block_pair(const uint8_t* __restrict__ blk0, bool second, uint8_t* tmp0, uint32_t tmp_stride, uint32_t* lz_scratch, int lane,
-							      Place&& place)
+							      Place&& place, const uint8_t* __restrict__ blk1 = nullptr)
 	{
 		constexpr uint32_t HS = (T + 1) / 2;
 		const int hb = lane >> 4, r = lane & 15;
 		const bool upper = hb && second;
 		const bool writer = !hb || second;
-		const uint8_t* blk = upper ? blk0 + T * 256 : blk0;
+		if (blk1 == nullptr)
+			blk1 = blk0 + T * 256; // the second block follows the first one (cvector buckets picked by id: anywhere)
+		const uint8_t* blk = upper ? blk1 : blk0;
 		const uint32_t below = (1u << r) - 1u; // rows before mine
 
 		uint32_t pw[T][4];
@@ -323,7 +325,7 @@ namespace sb
 				for (int hh = 0; hh < 2; ++hh) {
 					if (!((want >> (16 * hh)) & 1u) || (hh && !second))
 						continue;
-					const uint8_t* gs = blk0 + (size_t)hh * T * 256;
+					const uint8_t* gs = hh ? blk1 : blk0;
 					uint8_t* sl = tmp0 + (size_t)hh * tmp_stride;
 					const uint32_t fmax = __shfl_sync(FULL, full, 16 * hh);
 					uint32_t w[2 * T];

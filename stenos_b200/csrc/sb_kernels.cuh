@@ -380,6 +380,97 @@ namespace sb
 	}
 
 	// ------------------------------------------------------------------------------------------
+	// cvector buckets of ONE 256-element block, two per warp (stenos_b200_compress_buckets_async): the lane-per-row pair
+	// encoder first -- it assumes ample room -- and its result stands whenever the reference's room checks could not have
+	// fired for it: every check of block_compress.h:1214-1248 compares (bytes so far) + 16 or full + 8 T + 2 with the room,
+	// so "size + 8 T + 32 <= room" and "not an LZ block" (LZ is what the room decides about, :1214) make the exact and the
+	// ample-room encodings the same bytes.  Everything else -- incompressible buckets next to their slot's end, LZ blocks,
+	// the array's partial last bucket -- is redone by the room-exact encoder, one bucket per warp, as in the bucket mode of
+	// encode_frame_kernel.  Output as there: [code][csize:3][payload] at dst + i * bucket_stride, sizes[i] = 4 + csize.
+	// ------------------------------------------------------------------------------------------
+	constexpr int BUCKET_WARPS = 4;
+	template<int T>
+	__global__ void __launch_bounds__(BUCKET_WARPS * 32) encode_bucket_pairs_kernel(EncodeParams P)
+	{
+		using L = EncodeLayout<T, 1>;
+		constexpr uint32_t PER_WARP = 2u * L::STRIDE + L::LZ_STRIDE;
+		STENOS_DYN_SMEM(uint8_t, smem);
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, hb = lane >> 4;
+		uint8_t* slots = smem + (uint32_t)warp * PER_WARP;
+		uint32_t* lz_scratch = reinterpret_cast<uint32_t*>(slots + 2u * L::STRIDE);
+		const uint32_t n_pairs = (P.n_sb + 1u) / 2u;
+		const long long room = (long long)P.bucket_stride - 4;
+		for (uint32_t pr = blockIdx.x * BUCKET_WARPS + warp; pr < n_pairs; pr += gridDim.x * BUCKET_WARPS) {
+			uint64_t in_at[2];
+			uint32_t in_bytes[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i = 2u * pr + h;
+				in_at[h] = i < P.n_sb ? (uint64_t)(P.bucket_ids ? P.bucket_ids[i] : i) * P.sb_bytes : 0ull;
+				in_bytes[h] = (i < P.n_sb && in_at[h] < P.bytes) ? (uint32_t)min((uint64_t)P.sb_bytes, P.bytes - in_at[h]) : 0u;
+			}
+			const bool full0 = in_bytes[0] == L::BLOCK, full1 = in_bytes[1] == L::BLOCK;
+			uint32_t size[2] = { 0u, 0u };
+			bool done[2] = { false, false };
+			if (P.level != 0 && full0) {
+				const uint32_t sz = encode_block_pair<T>(P.src + in_at[0], full1, slots, L::STRIDE, lz_scratch, lane,
+									 [&](uint32_t) -> uint8_t* { return (hb && full1) ? slots + L::STRIDE : slots; }, P.src + in_at[1]);
+				__syncwarp();
+				const uint32_t s0 = __shfl_sync(FULL, sz, 0), s1 = __shfl_sync(FULL, sz, 16);
+				size[0] = s0;
+				size[1] = s1;
+				done[0] = (long long)s0 + 8 * T + 32 <= room && slots[0] != (uint8_t)MARK_LZ;
+				done[1] = full1 && (long long)s1 + 8 * T + 32 <= room && slots[L::STRIDE] != (uint8_t)MARK_LZ;
+			}
+#pragma unroll 1
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i = 2u * pr + h;
+				if (i >= P.n_sb)
+					break;
+				uint8_t* slot = slots + (uint32_t)h * L::STRIDE;
+				const uint8_t* in = P.src + in_at[h];
+				bool err = false;
+				uint32_t csize = size[h];
+				if (P.level == 0 || in_bytes[h] == 0u)
+					err = true; // level 0: COPY (stenos.cpp:432); an id past the array: reported below
+				else if (!done[h]) {
+					// the room-exact encoder (one warp per bucket)
+					__syncwarp();
+					const uint32_t r = room > 0 ? (uint32_t)room : 0u;
+					if (in_bytes[h] == L::BLOCK)
+						csize = encode_block<T, true>(in, slot, lz_scratch, lane, r, err);
+					else
+						csize = encode_partial_block<T, true>(in, in_bytes[h], slot, lane, r, err);
+					__syncwarp();
+				}
+				const bool copy = err || csize > in_bytes[h]; // stenos.cpp:609-610
+				const uint32_t len = copy ? in_bytes[h] : csize;
+				const uint32_t out_size = 4u + len;
+				if (out_size > P.bucket_stride || in_bytes[h] == 0u) {
+					if (lane == 0) {
+						atomicOr(&P.result[1], (unsigned long long)DEV_ERR_DST_OVERFLOW);
+						P.bucket_sizes[i] = 0u;
+					}
+					continue;
+				}
+				uint8_t* out = P.dst + (uint64_t)i * P.bucket_stride;
+				if (lane == 0) {
+					out[0] = (uint8_t)(copy ? CODE_COPY : CODE_BLOCK);
+					out[1] = (uint8_t)len;
+					out[2] = (uint8_t)(len >> 8);
+					out[3] = (uint8_t)(len >> 16);
+					P.bucket_sizes[i] = out_size;
+				}
+				if (copy)
+					warp_copy_bytes(out + 4, in, len, lane);
+				else
+					warp_copy_bytes(out + 4, slot, len, lane);
+			}
+			__syncwarp();
+		}
+	}
+
+	// ------------------------------------------------------------------------------------------
 	// frame index: offsets of the superblock headers of a frame that lives in device memory
 	// ------------------------------------------------------------------------------------------
 	struct IndexParams
