@@ -583,9 +583,30 @@ namespace sb
 			}
 			const uint64_t doff = (uint64_t)id * P.bucket_bytes;
 			const uint32_t dsize = valid ? (uint32_t)min((uint64_t)P.bucket_bytes, P.total - doff) : 0u;
-			const uint32_t e = decode_superblock_pair<T>(P.src, P.src_size, valid ? off : 0ull, dsize, P.dst + (uint64_t)(valid ? i : 0u) * P.bucket_bytes, valid, false, lz_scratch,
-								     lane, scratch_word);
-			bad |= e;
+			uint8_t* out = P.dst + (uint64_t)(valid ? i : 0u) * P.bucket_bytes;
+			// Buckets of ONE plane-coded block (cvector's default): straight to the row decoder, without the superblock
+			// machinery of decode_superblock_pair (header loop, block loop, special-block and tail paths: a third of the
+			// instructions of a one-block bucket).  Anything else -- COPY / LZ / marker blocks, a bucket near the end of
+			// the buffer, larger or partial buckets, a corrupt header -- takes the general path for the pair.
+			bool fast = false;
+			const uint8_t* q = P.src;
+			uint32_t csize = 0;
+			if (valid && dsize == (uint32_t)T * 256u && off + 4 <= P.src_size) {
+				const uint8_t* p = P.src + off;
+				csize = rd24(p + 1);
+				q = p + 4;
+				fast = p[0] == (uint8_t)CODE_BLOCK && off + 4 + csize <= P.src_size && csize > (uint32_t)(T + 1) / 2 && q + WorstBlock<T>::READ <= lim &&
+				       q[0] < (uint8_t)MARK_COPY;
+			}
+			if (__all_sync(FULL, fast || !valid)) {
+				const uint32_t c = decode_block_rows<T>(q, fast, r, 16 * half, out);
+				if (fast && (c == 0xFFFFFFFFu || c > csize))
+					bad |= DEV_ERR_INVALID_INPUT;
+			}
+			else {
+				const uint32_t e = decode_superblock_pair<T>(P.src, P.src_size, valid ? off : 0ull, dsize, out, valid, false, lz_scratch, lane, scratch_word);
+				bad |= e;
+			}
 			if (bad && (lane & 15) == 0)
 				atomicOr(&P.result[1], (unsigned long long)bad);
 		}

@@ -380,3 +380,35 @@ def test_other_element_sizes_multi_superblock(T):
     bad[8] = 9
     assert run(ctx.decompress, bytes(bad), T, 3000 * T) == "INVALID_INPUT"
     assert run(ctx.compress, raw_of(np.arange(495, dtype=np.uint8)), 9) == "INVALID_PARAMETER"
+
+
+@pytest.mark.parametrize("T", [2, 4, 8])
+def test_bucket_gather_fast_path_and_general_path(T):
+    """stenos_b200_gather_decode_async on a cvector-style frame (one block per bucket): plane-coded buckets take the row
+    decoder directly, COPY / LZ buckets and the partial last bucket the general superblock path; pairs mix both."""
+    ctx = api.Context(block_shift=0)
+    raw = _bucket_inputs(T, 21, seed=40 + T)
+    raw = np.concatenate([raw, raw[: 256 * T // 2 + T]])  # a partial last bucket
+    if T % 4 == 0:
+        lz = raw_of(dists.make("lz_pairs", 256, T, seed=1))
+        raw[5 * 256 * T:6 * 256 * T] = lz
+    frame = np.frombuffer(port.compress(raw, T, block_shift=0), dtype=np.uint8)
+    bb = 256 * T
+    n_b = (raw.size + bb - 1) // bb
+    offs = np.array(port.frame_index(frame, T), dtype=np.uint64)
+    assert offs.size == n_b + 1
+    ids = np.array(list(range(n_b)) + [3, 3, 0, n_b - 1, 7], dtype=np.uint32)
+    out = np.zeros(ids.size * bb, dtype=np.uint8)
+    res = np.zeros(2, dtype=np.uint64)
+    ctx.gather_decode_async(frame, frame.size, T, bb, raw.size, offs, n_b, ids, ids.size, out, res)
+    ctx.synchronize()
+    assert res[1] == 0
+    for k, b in enumerate(ids):
+        want = raw[int(b) * bb:(int(b) + 1) * bb]
+        assert out[k * bb:k * bb + want.size].tobytes() == want.tobytes(), (T, k, int(b))
+    # a damaged bucket is reported, the others still decode
+    bad = frame.copy()
+    bad[int(offs[1]) + 4 + (T + 1) // 2] ^= 0xFF  # plane 0's first header byte of bucket 1
+    ctx.gather_decode_async(bad, bad.size, T, bb, raw.size, offs, n_b, ids[:4], 4, out, res)
+    ctx.synchronize()
+    assert out[2 * bb:3 * bb].tobytes() == raw[2 * bb:3 * bb].tobytes()
