@@ -155,8 +155,9 @@ STENOS_B200_EXPORT size_t stenos_b200_delta_inv(stenos_context* ctx, size_t byte
 /* Hybrid level >= 2, first slice.  DECODING is complete: stenos_decompress[_generic] reads
  * every frame the reference writes at levels 2..9 for bytesoftype in {2,4,8} (superblock codes 2..5 of
  * stenos.cpp:34-39: Zstd on the host threads of stenos_set_threads, inverse filters and block decoder on the device).
- * ENCODING with a forced strategy: every superblock as code 3 (Zstd over the shuffled input, stenos.cpp:617-634) or
- * code 4 (Zstd over the shuffled + byte-delta input, :636-656), level in 2..9 (superblock size and Zstd level as the
+ * ENCODING with a forced strategy: every superblock as code 3 (Zstd over the shuffled input, stenos.cpp:617-634),
+ * code 4 (Zstd over the shuffled + byte-delta input, :636-656), level in 2..9, or code 5 (Zstd over the superblock's
+ * block stream, :560-603; level 2 only: the device block encoder holds 128 KiB superblocks) (superblock size and Zstd level as the
  * reference maps them); the reference's own choice between strategies (lz4_guess_ratio, :492-558) is not made here,
  * so stenos_compress with level >= 2 still returns STENOS_ERROR_INVALID_PARAMETER.  Where the reference picks the
  * forced strategy for every superblock the frames are identical.  Host or device pointers; synchronous. */

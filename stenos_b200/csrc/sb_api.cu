@@ -2254,8 +2254,11 @@ namespace
 	{
 		if (T == 0 || T >= STENOS_MAX_BYTESOFTYPE)
 			return STENOS_ERROR_INVALID_BYTESOFTYPE;
-		if (!supported_T(T) || level < 2 || level > 9 || (strategy != 3 && strategy != 4) || bytes % T != 0 || ctx->custom_shift != STENOS_NO_BLOCK_SHIFT || ctx->max_ns != 0)
+		if (!supported_T(T) || level < 2 || level > 9 || (strategy != 3 && strategy != 4 && strategy != 5) || bytes % T != 0 || ctx->custom_shift != STENOS_NO_BLOCK_SHIFT ||
+		    ctx->max_ns != 0)
 			return STENOS_ERROR_INVALID_PARAMETER;
+		if (strategy == 5 && level != 2)
+			return STENOS_ERROR_INVALID_PARAMETER; // the device block encoder holds superblocks of 128 KiB: level 2 (levels >= 3 use 256 KiB .. 2 MiB)
 		if (!ctx->activate())
 			return STENOS_ERROR_ALLOC;
 		if (!load_zstd() || !p_zstd_maxclevel)
@@ -2289,14 +2292,44 @@ namespace
 		if (bytes == 0)
 			goto done;
 		{
-			// ---- the filter on the device, back to the host
-			std::unique_ptr<uint8_t[]> filt(new (std::nothrow) uint8_t[bytes]);
-			if (!filt || !ctx->hyb.reserve(bytes + 32))
+			// ---- the device stage, back to the host: the filtered bytes (strategies 3 / 4), or every superblock's block stream
+			// (strategy 5, stenos.cpp:560-603: block_compress_generic into a buffer of `bytes` bytes -- the bucket mode of the
+			// block encoder with a slot of 4 + bytes per superblock reproduces that room; then Zstd over the stream)
+			const size_t stride5 = sb + 4;
+			const size_t stage_bytes = strategy == 5 ? n_sb * stride5 : bytes;
+			std::unique_ptr<uint8_t[]> filt(new (std::nothrow) uint8_t[stage_bytes]);
+			if (!filt || !ctx->hyb.reserve(stage_bytes + 32))
 				return STENOS_ERROR_ALLOC;
-			const size_t fr = filter_impl(ctx, OP_SHUFFLE, T, bytes, sb, src, ctx->hyb.p, strategy == 4 ? 1 : 0);
-			if (is_err(fr))
-				return fr;
-			cudaMemcpyAsync(filt.get(), ctx->hyb.p, bytes, cudaMemcpyDeviceToHost, st);
+			if (strategy == 5) {
+				const uint8_t* d_in = src;
+				if (!src_dev || ((uintptr_t)src & 15u)) {
+					if (!ctx->in.reserve(bytes + 32))
+						return STENOS_ERROR_ALLOC;
+					cudaMemcpyAsync(ctx->in.p, src, bytes, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+					d_in = ctx->in.p;
+				}
+				if (!ctx->hoffs.reserve(n_sb * 4 + 64) || !ctx->ctl.reserve(64))
+					return STENOS_ERROR_ALLOC;
+				unsigned int* d_sizes = reinterpret_cast<unsigned int*>(ctx->hoffs.p);
+				unsigned long long* d_res = reinterpret_cast<unsigned long long*>(ctx->ctl.p);
+				const int saved_level = ctx->level;
+				ctx->level = 1; // the block level of every level >= 1 (stenos.cpp:430, block_compress.h:1122-1124)
+				const size_t n_full = bytes / sb, last = bytes - n_full * sb;
+				size_t br = 0;
+				if (n_full)
+					br = stenos_b200_compress_buckets_async(ctx, d_in, T, sb, n_full * sb, nullptr, n_full, ctx->hyb.p, stride5, d_sizes, d_res);
+				if (!is_err(br) && last >= 128) // the partial last superblock: its own room (4 + its bytes)
+					br = stenos_b200_compress_buckets_async(ctx, d_in + n_full * sb, T, sb, last, nullptr, 1, ctx->hyb.p + n_full * stride5, last + 4, d_sizes + n_full, d_res);
+				ctx->level = saved_level;
+				if (is_err(br))
+					return br;
+			}
+			else {
+				const size_t fr = filter_impl(ctx, OP_SHUFFLE, T, bytes, sb, src, ctx->hyb.p, strategy == 4 ? 1 : 0);
+				if (is_err(fr))
+					return fr;
+			}
+			cudaMemcpyAsync(filt.get(), ctx->hyb.p, stage_bytes, cudaMemcpyDeviceToHost, st);
 			if (cudaStreamSynchronize(st) != cudaSuccess) {
 				cudaGetLastError();
 				return STENOS_ERROR_UNDEFINED;
@@ -2328,19 +2361,39 @@ namespace
 					const uint8_t* in = filt.get() + i * sb;
 					unsigned code = (unsigned)strategy;
 					int zl = zlevel;
+					size_t zn = n; // bytes that go through Zstd
 					if (n < 128) { // stenos.cpp:435-437: a tiny superblock is Zstd on the raw bytes, zstd_level 0 -> 1
 						in = raw_of(i, n, tmp);
 						code = (unsigned)CODE_ZSTD;
 						zl = 1;
 					}
-					const size_t cap = n + n / 128 + 512;
-					pc.z.reset(new (std::nothrow) uint8_t[cap]);
+					else if (strategy == 5) {
+						const uint8_t* slot = filt.get() + i * stride5;
+						const size_t cs = (size_t)slot[1] | ((size_t)slot[2] << 8) | ((size_t)slot[3] << 16);
+						if (slot[0] == (uint8_t)CODE_BLOCK && cs <= n) {
+							in = slot + 4;
+							zn = cs;
+						}
+						else {
+							// the block coding did not shrink the superblock (:564-572): the reference now picks a Zstd strategy by its
+							// LZ4 estimates; the forced strategy falls back to the one it takes when they are low, direct Zstd (:658)
+							in = raw_of(i, n, tmp);
+							code = (unsigned)CODE_ZSTD;
+						}
+					}
+					const size_t cap = zn + zn / 128 + 512;
+					pc.z.reset(new (std::nothrow) uint8_t[std::max(cap, n)]);
 					if (!pc.z) {
 						failed.store(STENOS_ERROR_ALLOC);
 						return;
 					}
-					const size_t zr = p_zstd_compress(pc.z.get(), cap, in, n, zl);
-					if (p_zstd_iserror(zr) || zr > n) { // :627-628 -> MEMCPY (:363-374)
+					const size_t zr = p_zstd_compress(pc.z.get(), cap, in, zn, zl);
+					if (code == 5u && (p_zstd_iserror(zr) || zr > zn)) { // :586-596 NO_ZSTD: the block stream as it is, code 1
+						memcpy(pc.z.get(), in, zn);
+						pc.len = zn;
+						pc.code = (unsigned)CODE_BLOCK;
+					}
+					else if (p_zstd_iserror(zr) || zr > n) { // :627-628 -> MEMCPY (:363-374)
 						const uint8_t* raw = raw_of(i, n, tmp);
 						memcpy(pc.z.get(), raw, n);
 						pc.len = n;

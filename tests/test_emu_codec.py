@@ -358,8 +358,21 @@ def test_forced_strategy_frames_equal_the_reference_where_it_picks_that_strategy
                     assert ref.decompress(got, T, raw.size) == raw.tobytes(), (name, level, strat)
                     assert ctx.decompress(np.frombuffer(got, dtype=np.uint8), T, raw.size) == raw.tobytes()
     assert hits[3] >= 1 and hits[4] >= 8, hits
+    # strategy 5 (Zstd over the block stream, stenos.cpp:560-603) at level 2: the block encoder with the room of `bytes` per superblock
+    hits5 = 0
+    for name, T, raw in dists.hybrid_cases(60000):
+        want = ref.compress(raw, T, level=2)
+        codes = dists.superblock_codes(np.frombuffer(want, dtype=np.uint8), T, raw.size)
+        got = ctx.compress_strategy(raw, T, 2, 5)
+        if set(codes) <= {5, 1}:
+            assert got == want, name
+            hits5 += 1
+        else:
+            assert ref.decompress(got, T, raw.size) == raw.tobytes(), name
+    assert hits5 >= 3, hits5
+    assert run(ctx.compress_strategy, raw_of(np.arange(100000, dtype=np.int32)), 4, 3, 5) == "INVALID_PARAMETER"  # strategy 5: level 2 only
     assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 1, 4) == "INVALID_PARAMETER"
-    assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 3, 5) == "INVALID_PARAMETER"
+    assert run(ctx.compress_strategy, raw_of(np.arange(1000, dtype=np.int32)), 4, 3, 6) == "INVALID_PARAMETER"
     assert run(ctx.compress_strategy, raw_of(np.arange(100000, dtype=np.int32)), 4, 3, 4, 100) == "DST_OVERFLOW"
 
 

@@ -642,3 +642,16 @@ def test_forced_strategy_frames_equal_the_reference_where_it_picks_that_strategy
         r = capi.lib().stenos_b200_compress_strategy(ctx._h, d_src.data_ptr(), T, raw.size, d_dst.data_ptr(), d_dst.numel(), 5, 4)
         assert r == len(ctx.compress_strategy(raw, T, 5, 4)) and bytes(d_dst[:r].cpu().numpy()) == ctx.compress_strategy(raw, T, 5, 4)
     assert hits >= 12, hits
+    # strategy 5 at level 2 (Zstd over the block stream, stenos.cpp:560-603): the config-2 / config-4 integer arrays
+    hits5 = 0
+    for name, T in (("int32_ramp_runs", 4), ("int64_ramp_runs", 8), ("int16_sine", 2)):
+        raw = raw_of(synth.make(name, (5 << 20) // T + 999))
+        want = ref.compress(raw, T, level=2, threads=4)
+        codes = dists.superblock_codes(np.frombuffer(want, dtype=np.uint8), T, raw.size)
+        got = ctx.compress_strategy(raw, T, 2, 5)
+        if set(codes) <= {5, 1}:
+            assert got == want, name
+            hits5 += 1
+        assert ref.decompress(got, T, raw.size) == raw.tobytes()
+        assert ctx.decompress(np.frombuffer(got, dtype=np.uint8), T, raw.size) == raw.tobytes()
+    assert hits5 >= 2, hits5
