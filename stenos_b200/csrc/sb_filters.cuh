@@ -306,6 +306,18 @@ namespace sb
 		const uint8_t* src = P.src + c * P.chunk;
 		uint8_t* dst = P.dst + c * P.chunk;
 		const uint64_t i1 = min(i0 + 16, cb);
+		// whole 16-byte groups with no stream start inside: one 128-bit load, the byte before the group, four SIMD byte
+		// subtractions, one 128-bit store (the byte-wise loop below was all there was before)
+		const uint64_t q = cb > 2048 ? cb / 4 : ~0ull;
+		const bool start_inside = i0 == 0 || (q != ~0ull && ((q - i0 < 16ull) || (2 * q - i0 < 16ull) || (3 * q - i0 < 16ull)));
+		if (i1 - i0 == 16 && !start_inside && (((uintptr_t)(src + i0) | (uintptr_t)(dst + i0)) & 15u) == 0) {
+			const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
+			const uint32_t a[4] = { v.x, v.y, v.z, v.w };
+			uint32_t d[4];
+			row_deltas(a, (uint32_t)src[i0 - 1] << 24, d);
+			*reinterpret_cast<uint4*>(dst + i0) = make_uint4(d[0], d[1], d[2], d[3]);
+			return;
+		}
 		for (uint64_t i = i0; i < i1; ++i)
 			dst[i] = delta_stream_start(i, cb) ? src[i] : (uint8_t)(src[i] - src[i - 1]);
 	}

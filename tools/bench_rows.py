@@ -104,6 +104,15 @@ def row_filters(T, name, nbytes, chunk, dev, pk, steps=5, warmup=3):
         out["shuffle%s_frac" % tag] = 2 * nbytes / t_s / 1e6 / pk
         out["unshuffle%s_ms" % tag] = t_u
         out["unshuffle%s_frac" % tag] = 2 * nbytes / t_u / 1e6 / pk
+    if T == 2:  # the plain byte delta and its inverse (no transpose; stenos::delta / delta_inv on every chunk), measured once
+        t_d = timeit(lambda: api.check(lib.stenos_b200_delta(ctx._h, nbytes, chunk, d_src.data_ptr(), d_a.data_ptr()), "delta"), steps, warmup)
+        t_i = timeit(lambda: api.check(lib.stenos_b200_delta_inv(ctx._h, nbytes, chunk, d_a.data_ptr(), d_b.data_ptr()), "delta_inv"), steps, warmup)
+        ok = ok and torch.equal(d_b, d_src)
+        for k in picks:
+            raw = d_src[k * chunk:(k + 1) * chunk].cpu().numpy()
+            ok = ok and d_a[k * chunk:(k + 1) * chunk].cpu().numpy().tobytes() == port.delta(raw)
+        out["delta_ms"], out["delta_frac"] = t_d, 2 * nbytes / t_d / 1e6 / pk
+        out["delta_inv_ms"], out["delta_inv_frac"] = t_i, 2 * nbytes / t_i / 1e6 / pk
     out["parity"] = bool(ok)
     ctx.close()
     return out
