@@ -1949,7 +1949,7 @@ namespace
 			}
 			else {
 				const uint64_t groups = nchunks * ((chunk + 15) / 16);
-				STENOS_LAUNCH(delta_kernel, dim3((unsigned)((groups + FILTER_THREADS - 1) / FILTER_THREADS)), dim3(FILTER_THREADS), 0, st, Q);
+				STENOS_LAUNCH(delta_kernel, dim3((unsigned)((groups + FILTER_THREADS * DELTA_GROUPS - 1) / (FILTER_THREADS * DELTA_GROUPS))), dim3(FILTER_THREADS), 0, st, Q);
 			}
 			++g_launches;
 		};

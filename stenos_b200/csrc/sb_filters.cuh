@@ -290,36 +290,44 @@ namespace sb
 		}
 	}
 
-	// plain delta (no transpose): one thread per 16 output bytes
+	// plain delta (no transpose): a thread handles DELTA_GROUPS groups of 16 output bytes, FILTER_THREADS groups apart (one CTA:
+	// 16 KiB -- with one group per thread, 4 GiB were a million 4 KiB CTAs and 0.58 of HBM bandwidth)
+	constexpr int DELTA_GROUPS = 4;
 	__global__ void __launch_bounds__(FILTER_THREADS) delta_kernel(FilterParams P)
 	{
 		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
 		const uint64_t groups_per_chunk = (P.chunk + 15) / 16;
-		const uint64_t g = (uint64_t)blockIdx.x * FILTER_THREADS + threadIdx.x;
-		const uint64_t c = g / groups_per_chunk;
-		if (c >= nchunks)
-			return;
-		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
-		const uint64_t i0 = (g - c * groups_per_chunk) * 16;
-		if (i0 >= cb)
-			return;
-		const uint8_t* src = P.src + c * P.chunk;
-		uint8_t* dst = P.dst + c * P.chunk;
-		const uint64_t i1 = min(i0 + 16, cb);
-		// whole 16-byte groups with no stream start inside: one 128-bit load, the byte before the group, four SIMD byte
-		// subtractions, one 128-bit store (the byte-wise loop below was all there was before)
-		const uint64_t q = cb > 2048 ? cb / 4 : ~0ull;
-		const bool start_inside = i0 == 0 || (q != ~0ull && ((q - i0 < 16ull) || (2 * q - i0 < 16ull) || (3 * q - i0 < 16ull)));
-		if (i1 - i0 == 16 && !start_inside && (((uintptr_t)(src + i0) | (uintptr_t)(dst + i0)) & 15u) == 0) {
-			const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
-			const uint32_t a[4] = { v.x, v.y, v.z, v.w };
-			uint32_t d[4];
-			row_deltas(a, (uint32_t)src[i0 - 1] << 24, d);
-			*reinterpret_cast<uint4*>(dst + i0) = make_uint4(d[0], d[1], d[2], d[3]);
-			return;
+		// (chunks are powers of two in practice -- 128 KiB << shift: a shift instead of a 64-bit division)
+		const bool pow2 = (groups_per_chunk & (groups_per_chunk - 1)) == 0;
+		const int sh = 63 - __clzll((long long)groups_per_chunk);
+#pragma unroll
+		for (int u = 0; u < DELTA_GROUPS; ++u) {
+			const uint64_t g = ((uint64_t)blockIdx.x * DELTA_GROUPS + u) * FILTER_THREADS + threadIdx.x;
+			const uint64_t c = pow2 ? g >> sh : g / groups_per_chunk;
+			if (c >= nchunks)
+				continue;
+			const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk);
+			const uint64_t i0 = (g - c * groups_per_chunk) * 16;
+			if (i0 >= cb)
+				continue;
+			const uint8_t* src = P.src + c * P.chunk;
+			uint8_t* dst = P.dst + c * P.chunk;
+			const uint64_t i1 = min(i0 + 16, cb);
+			// whole 16-byte groups with no stream start inside: one 128-bit load, the byte before the group, four SIMD byte
+			// subtractions, one 128-bit store
+			const uint64_t q = cb > 2048 ? cb / 4 : ~0ull;
+			const bool start_inside = i0 == 0 || (q != ~0ull && ((q - i0 < 16ull) || (2 * q - i0 < 16ull) || (3 * q - i0 < 16ull)));
+			if (i1 - i0 == 16 && !start_inside && (((uintptr_t)(src + i0) | (uintptr_t)(dst + i0)) & 15u) == 0) {
+				const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
+				const uint32_t a[4] = { v.x, v.y, v.z, v.w };
+				uint32_t d[4];
+				row_deltas(a, (uint32_t)src[i0 - 1] << 24, d);
+				*reinterpret_cast<uint4*>(dst + i0) = make_uint4(d[0], d[1], d[2], d[3]);
+				continue;
+			}
+			for (uint64_t i = i0; i < i1; ++i)
+				dst[i] = delta_stream_start(i, cb) ? src[i] : (uint8_t)(src[i] - src[i - 1]);
 		}
-		for (uint64_t i = i0; i < i1; ++i)
-			dst[i] = delta_stream_start(i, cb) ? src[i] : (uint8_t)(src[i] - src[i - 1]);
 	}
 
 	// inverse delta (delta.cpp:230-267): one CTA per (chunk, stream); the stream is scanned tile by tile (16 bytes per
