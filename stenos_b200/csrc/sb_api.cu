@@ -1897,7 +1897,8 @@ namespace
 	{
 		const uint64_t nchunks = (P.bytes + P.chunk - 1) / P.chunk;
 		const uint64_t groups_per_chunk = (P.chunk / T + 15) / 16 + 1; // + the group that copies the leftover bytes
-		const uint64_t ctas_per_chunk = (groups_per_chunk + FILTER_THREADS - 1) / FILTER_THREADS;
+		const uint64_t per_cta = (uint64_t)FILTER_THREADS * (inverse ? 1 : ShuffleGroups<T>::N); // groups a CTA handles
+		const uint64_t ctas_per_chunk = (groups_per_chunk + per_cta - 1) / per_cta;
 		FilterParams Q = P;
 		Q.chunk_in_y = nchunks <= 65535 ? 1u : 0u; // grid.y is limited to 65535; one of the two always fits
 		const dim3 grid = Q.chunk_in_y ? dim3((unsigned)ctas_per_chunk, (unsigned)nchunks) : dim3((unsigned)nchunks, (unsigned)ctas_per_chunk);

@@ -157,17 +157,34 @@ namespace sb
 
 	constexpr int FILTER_THREADS = 256;
 
+	// groups of 16 elements a thread of shuffle_kernel handles, FILTER_THREADS groups apart: small elements make small CTAs
+	// (T = 2: 8 KiB per CTA with one group per thread; the fused delta sat at 0.78 of HBM bandwidth)
+	template<int T>
+	struct ShuffleGroups
+	{
+		static constexpr int N = T == 2 ? 4 : (T == 4 ? 2 : 1);
+	};
+
+	template<int T>
+	__device__ __forceinline__ void shuffle_group(const FilterParams& P, const uint8_t* src, uint8_t* dst, uint64_t cb, uint64_t n, uint64_t j0);
+
 	// shuffle (+ optional fused delta).  grid.x covers groups of 16 elements of every chunk.
 	template<int T>
 	__global__ void __launch_bounds__(FILTER_THREADS) shuffle_kernel(FilterParams P)
 	{
-		// grid: x = chunk, y * FILTER_THREADS + thread = group of 16 elements inside the chunk (+ one group for the leftover bytes)
+		// grid: x = chunk, (y * N + u) * FILTER_THREADS + thread = group of 16 elements inside the chunk (+ one group for the leftover bytes)
 		const uint64_t c = P.chunk_in_y ? blockIdx.y : blockIdx.x;
 		const uint64_t cb = min(P.chunk, P.bytes - c * P.chunk); // bytes of this chunk
 		const uint64_t n = cb / T;                                // elements
-		const uint64_t j0 = ((uint64_t)(P.chunk_in_y ? blockIdx.x : blockIdx.y) * FILTER_THREADS + threadIdx.x) * 16; // first element of this thread
 		const uint8_t* src = P.src + c * P.chunk;
 		uint8_t* dst = P.dst + c * P.chunk;
+#pragma unroll 1
+		for (int u = 0; u < ShuffleGroups<T>::N; ++u)
+			shuffle_group<T>(P, src, dst, cb, n, (((uint64_t)(P.chunk_in_y ? blockIdx.x : blockIdx.y) * ShuffleGroups<T>::N + u) * FILTER_THREADS + threadIdx.x) * 16);
+	}
+	template<int T>
+	__device__ __forceinline__ void shuffle_group(const FilterParams& P, const uint8_t* src, uint8_t* dst, uint64_t cb, uint64_t n, uint64_t j0)
+	{
 		if (j0 >= n) {
 			// the thread after the last group copies the leftover bytes (shuffle-generic.h:73)
 			if (j0 < n + 16) {
