@@ -1982,9 +1982,9 @@ namespace
 						FilterParams F = P;
 						F.bytes = fused_chunks * chunk;
 						switch (T) {
-							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 2 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
-							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 4 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
-							case 8: STENOS_LAUNCH(unshuffle_delta_kernel<8>, dim3((unsigned)fused_chunks), dim3(UNSHUFFLE_DELTA_THREADS), 256 + 8 * 16 * UNSHUFFLE_DELTA_THREADS, st, F); break;
+							case 2: STENOS_LAUNCH(unshuffle_delta_kernel<2>, dim3((unsigned)fused_chunks), dim3(UnshuffleDeltaThreads<2>::N), 256 + 2 * 16 * UnshuffleDeltaThreads<2>::N, st, F); break;
+							case 4: STENOS_LAUNCH(unshuffle_delta_kernel<4>, dim3((unsigned)fused_chunks), dim3(UnshuffleDeltaThreads<4>::N), 256 + 4 * 16 * UnshuffleDeltaThreads<4>::N, st, F); break;
+							case 8: STENOS_LAUNCH(unshuffle_delta_kernel<8>, dim3((unsigned)fused_chunks), dim3(UnshuffleDeltaThreads<8>::N), 256 + 8 * 16 * UnshuffleDeltaThreads<8>::N, st, F); break;
 						}
 						++g_launches;
 					}

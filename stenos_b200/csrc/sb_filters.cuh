@@ -434,13 +434,26 @@ namespace sb
 	// is an affine map last = a * prev + c with a = 0 if it holds a restart, and the CTA scans maps, two planes per
 	// register (compose_maps2).  Requires cb % (16 * T) == 0 and 16-byte aligned chunks (the host checks).
 	// ------------------------------------------------------------------------------------------
-#ifndef UNSHUFFLE_DELTA_NT
-#define UNSHUFFLE_DELTA_NT 128 // measured: 128 > 256 > 512 > 1024 threads (more CTAs per SM, cheaper barriers)
-#endif
-	constexpr int UNSHUFFLE_DELTA_THREADS = UNSHUFFLE_DELTA_NT;
+	// threads of a CTA (one CTA per chunk).  Measured with the next tile staged by cp.async, 2N/t over HBM bandwidth at
+	// 256 KiB chunks: 256 threads 0.83 / 0.82 / 0.59 (T = 2 / 4 / 8), 128: 0.85 / 0.89 / 0.63, 64: 0.86 / 0.92 / 0.63,
+	// 32: 0.81 / 0.91 / 0.65 -- small CTAs: more of them per SM, cheap barriers.
+#ifdef UNSHUFFLE_DELTA_NT
 	template<int T>
-	__global__ void __launch_bounds__(UNSHUFFLE_DELTA_THREADS) unshuffle_delta_kernel(FilterParams P)
+	struct UnshuffleDeltaThreads
 	{
+		static constexpr int N = UNSHUFFLE_DELTA_NT;
+	};
+#else
+	template<int T>
+	struct UnshuffleDeltaThreads
+	{
+		static constexpr int N = T == 8 ? 32 : 64;
+	};
+#endif
+	template<int T>
+	__global__ void __launch_bounds__(UnshuffleDeltaThreads<T>::N) unshuffle_delta_kernel(FilterParams P)
+	{
+		constexpr int UNSHUFFLE_DELTA_THREADS = UnshuffleDeltaThreads<T>::N;
 		constexpr int NW = UNSHUFFLE_DELTA_THREADS / 32;
 		constexpr int NP = T / 2; // plane pairs
 		STENOS_DYN_SMEM(uint32_t, warp_maps_raw); // [NP][NW] (256 bytes reserved), then the staging slots of the next tile
