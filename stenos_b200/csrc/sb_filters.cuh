@@ -351,7 +351,10 @@ namespace sb
 	// thread, one 128-bit load and store each) with a running carry.  Per tile: byte sums of the 16-byte groups
 	// (VABSDIFF4), one CTA-wide scan of them, then the in-group prefix sums on top of the group's carry
 	// (prefix16: 16-bit lanes, one IMAD per word).
-	constexpr int DELTA_INV_THREADS = 1024;
+#ifndef DELTA_INV_NT
+#define DELTA_INV_NT 128
+#endif
+	constexpr int DELTA_INV_THREADS = DELTA_INV_NT; // (1024 until round 2: four barriers of 32 warps per 16 KiB tile)
 	__global__ void __launch_bounds__(DELTA_INV_THREADS) delta_inv_kernel(FilterParams P)
 	{
 		STENOS_DYN_SMEM(uint32_t, warp_sums);
@@ -407,7 +410,7 @@ namespace sb
 			if (lane == 31)
 				warp_sums[warp] = incl;
 			__syncthreads();
-			const uint32_t ws = warp_sums[lane]; // DELTA_INV_THREADS / 32 == 32 warps
+			const uint32_t ws = lane < DELTA_INV_THREADS / 32 ? warp_sums[lane] : 0u;
 			const uint32_t wpre = __reduce_add_sync(FULL, lane < warp ? ws : 0u);
 			const uint32_t tot = __reduce_add_sync(FULL, ws);
 			__syncthreads();
